@@ -1,0 +1,311 @@
+#!/usr/bin/env python3
+"""Benchmark of the PMR446 receive chain on B200 (BASELINE.json metric: IQ Msamples/s through the
+full chain + roofline fraction).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[2]; configs[4] is the same shard per GPU at N = 8): a batch of
+STREAMS = 1024 independent 2.4 Msps cu8 PMR446 captures per GPU, all 16 channels demodulated to s16
+audio.  One step = one second of signal of every stream (2.4 M samples x 1024 streams = 2.46 G
+samples, 4.9 GB of input per GPU -- far larger than the 126 MB L2, so no L2 flush is needed between
+steps).  Filter state carries from step to step exactly as in streaming use.
+
+  value     device-resident throughput: inputs already in HBM, s16 audio left in HBM; K steps timed with
+            CUDA events on the launch stream between barriers, max over ranks.
+  e2e       the same K steps through the host-buffer C-ABI call pmr446_batch_execute(): pinned host IQ
+            -> H2D -> chain -> D2H of the s16 audio, copies inside the timed region.
+  roofline  the dominant kernel (audio_kernel: 377-tap high-pass FIR + de-emphasis + s16), timed live with
+            CUDA events inside the timed steps; algorithmic FLOPs / measured FP32 FFMA peak.
+  cpu_baseline  the CPU oracle (port of the reference chain, all 16 channels) on all host cores.
+
+--impl reference times the reference's CPU chain (the oracle port -- the reference itself cannot be
+built here) on the host cores with the same config/metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+FS = 2400000
+CHUNK = 2400000            # one second of signal per step
+STREAMS = int(os.environ.get("PMR446_BENCH_STREAMS", "1024"))
+METRIC = "IQ Msamples/s through full PMR446 chain"
+UNIT = "Msamples/s"
+# algorithmic work of the 2.4 Msps / 16-channel chain
+FLOP_PER_SAMPLE = 122.1
+BYTES_PER_SAMPLE = 2.17
+AUDIO_FLOP_PER_OUT = 377 * 2 + 5   # HP FIR (2 flop per tap) + gain + de-emphasis, per 12.5 kHz channel sample
+WORKLOAD = "configs[2]: %d independent 2.4 Msps cu8 PMR446 captures x 16 channels per GPU, 1 s of signal per step" % STREAMS
+
+
+def config_dict(n_gpus):
+    return {"workload": WORKLOAD, "streams_per_gpu": STREAMS, "fs_in": FS, "samples_per_stream_per_step": CHUNK,
+            "channels": 16, "in_fmt": "cu8", "out": "s16 audio, 16 x 12.5 kHz per stream", "parallelism": "streams sharded, %d GPU(s)" % n_gpus,
+            "l2": "inputs (4.9 GB/step/GPU) larger than L2; no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------
+def make_base_captures(count, n):
+    from sdr_pmr446_b200 import synth
+    return [synth.make_cu8(synth.CaptureSpec(fs=float(FS), carriers=synth.rotated_carriers(s)), n, 446 + s) for s in range(count)]
+
+
+def cpu_chain_rate(threads, seconds_of_signal, active_only=-1):
+    """Oracle (CPU port of the reference chain) on `threads` host threads, one stream each.  Returns
+    (Msamples/s aggregate, wall seconds)."""
+    from oracle import oracle as orc
+    base = make_base_captures(min(threads, 4), CHUNK)
+    objs = [orc.PmrOracle(fs_in=FS, in_fmt=1, audio_gain=1.0, chunk=CHUNK, active_only=active_only) for _ in range(threads)]
+
+    def work(i):
+        for _ in range(seconds_of_signal):
+            objs[i].execute(base[i % len(base)], want=("pcm",))
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    for o in objs:
+        o.close()
+    return threads * seconds_of_signal * CHUNK / dt / 1e6, dt
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, reasons = [], None, set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        top = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": (top[len(top) // 2] if top else None), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    secs = 1
+    vals = []
+    for it in range(args.warmup + args.steps):
+        v, dt = cpu_chain_rate(cores, secs)
+        if it >= args.warmup:
+            vals.append((v, dt))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([dt for _, dt in vals]) * 1e3)
+    sample = "%d host threads x %d s of one 2.4 Msps stream each per step (all 16 channels demodulated)" % (cores, secs)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config_dict(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference = CPU oracle port of the liquid-dsp chain (reference cannot be compiled here: liquid-dsp v1.7.0 absent)"}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from sdr_pmr446_b200 import chain
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=dev)
+
+    S, n = STREAMS, CHUNK
+    # synthetic captures: 8 distinct seeded captures, circularly shifted per stream
+    base = make_base_captures(8, n)
+    base_t = [torch.from_numpy(b) for b in base]
+    iq_host = torch.empty((S, 2 * n), dtype=torch.uint8).pin_memory()
+    for s in range(S):
+        sh = 2 * 16 * ((s // 8) + rank * (S // 8))
+        iq_host[s, :2 * n - sh] = base_t[s % 8][sh:]
+        iq_host[s, 2 * n - sh:] = base_t[s % 8][:sh]
+    iq_dev = iq_host.to(dev, non_blocking=True)
+    batch = chain.PmrBatch(n_streams=S, device=local_rank, fs_in=FS, in_fmt=1, audio_gain=1.0, max_chunk=n)
+    ld = batch.max_ns
+    pcm_dev = torch.empty((S, 16, ld), dtype=torch.int16, device=dev)
+    outs = {"pcm": pcm_dev, "ld": ld}
+    torch.cuda.synchronize()
+    fp32_peak = chain.measure_fp32_peak()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm ("value") ----------------
+    launches = 0
+    for _ in range(args.warmup):
+        batch.execute_device(iq_dev, n, outs)
+    batch.timing(True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        batch.execute_device(iq_dev, n, outs)
+        launches += batch.last_launches
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    timings = batch.get_timings()
+    batch.timing(False)
+    checksum = int(pcm_dev[:, :, :12500].to(torch.int64).abs().sum().item())
+
+    # ---------------- end-to-end arm ("e2e"): host buffers through the C ABI ----------------
+    pcm_host = np.zeros((S, 16, ld), np.int16)
+    pcm_host_t = torch.from_numpy(pcm_host).pin_memory()
+    pcm_host = pcm_host_t.numpy()
+    iq_np = iq_host.numpy()
+    import ctypes as C
+    from sdr_pmr446_b200._lib import Outputs, check, lib
+    o = Outputs()
+    o.ld, o.res_ld, o.pcm = ld, batch.max_res, pcm_host.ctypes.data
+    ny, ns = C.c_uint(0), C.c_uint(0)
+    e2e_steps = max(1, min(args.steps, 5))
+
+    def e2e_step():
+        check(lib().pmr446_batch_execute(batch.h, iq_np.ctypes.data, iq_np.strides[0], n, C.byref(o), C.byref(ny), C.byref(ns)),
+              "pmr446_batch_execute")
+
+    for _ in range(min(args.warmup, 2)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_ns = ns.value
+
+    # ---------------- reduce over ranks ----------------
+    red = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        stats = torch.tensor([float(checksum)], dtype=torch.float64, device=dev)
+        gathered = [torch.zeros_like(stats) for _ in range(world)]
+        dist.all_gather(gathered, stats)   # NCCL is used for statistics only; the data path has no collective
+    ms_total, e2e_ms = float(red[0].item()), float(red[1].item())
+    total_samples = float(world) * S * n * args.steps
+    value = total_samples / (ms_total * 1e-3) / 1e6
+    e2e_value = float(world) * S * n * e2e_steps / (e2e_ms * 1e-3) / 1e6
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        a_ms, a_cnt = timings.get("audio", (0.0, 0))
+        a_avg = a_ms / max(a_cnt, 1)
+        a_flops = AUDIO_FLOP_PER_OUT * float(S) * 16 * 12500
+        a_tflops = a_flops / (a_avg * 1e-3) / 1e12 if a_avg > 0 else 0.0
+        step_ms = ms_total / args.steps
+        shares = {k: round(v[0] / max(v[1], 1) / step_ms, 4) for k, v in timings.items()}
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "audio_kernel_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        cores = os.cpu_count() or 1
+        cpu_v, cpu_dt = cpu_chain_rate(cores, 2)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": S * n * 2, "d2h_bytes_per_step": S * 16 * int(e2e_ns) * 2,
+                    "steps": e2e_steps, "api": "pmr446_batch_execute (host buffers, pinned)"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"kernel": "audio_kernel (377-tap CTCSS high-pass FIR + de-emphasis + s16)", "bound": "fp32", "achieved": a_tflops,
+                         "peak": fp32_peak, "unit": "TFLOP/s", "frac": a_tflops / fp32_peak if fp32_peak else None, "traffic": traffic,
+                         "peak_source": "FFMA issue peak measured live by pmr446_measure_fp32_peak (MEASURED_PEAKS.json has no FP32 figure)",
+                         "avg_launch_ms": a_avg, "share_of_step": shares.get("audio")},
+            "chain_roofline": {"fp32": {"flop_per_sample": FLOP_PER_SAMPLE, "achieved_tflops": value * 1e6 * FLOP_PER_SAMPLE / 1e12 / world,
+                                        "peak_tflops": fp32_peak, "frac": value * 1e6 * FLOP_PER_SAMPLE / 1e12 / world / fp32_peak},
+                               "hbm": {"bytes_per_sample": BYTES_PER_SAMPLE, "achieved_gbs": value * 1e6 * BYTES_PER_SAMPLE / 1e9 / world,
+                                       "peak_gbs": peaks.get("hbm_gbs"), "frac": value * 1e6 * BYTES_PER_SAMPLE / 1e9 / world / peaks.get("hbm_gbs"),
+                                       "peak_source": peak_src}},
+            "kernel_share_of_step": shares,
+            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d host threads x 2 s of one 2.4 Msps stream each (all 16 channels demodulated), %.1f s wall" % (cores, cpu_dt)},
+            "checksum": checksum,
+        }
+        print(json.dumps(line), flush=True)
+    batch.close()
+    if distributed:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,296 @@
+// Waterfall (asgram / spgram) kernels -- replaces asgramcf_write + asgramcf_execute of the
+// reference (/root/reference/src/sdr_pmr446.c:473-477, :910-913).
+//
+// Per chunk and stream: Welch periodogram of the UN-mixed resampler output with a Hann window
+// of length W, hop W/2, zero-padded nfft = 4W transform (W is the terminal width, so nfft is in
+// general not a power of two: 480 for W = 120, 6400 for W = 1600), |X|^2 summed over the chunk,
+// then dB, fft-shift, peak search, 4-bin column reduction and the 10-level character map.
+// The FFT is a shared-memory Stockham autosort with radices 4/2/3/5 (any other prime factor
+// falls back to a generic radix-p butterfly); one block walks the transforms of one
+// (stream, part) and keeps the |X|^2 accumulator in shared memory.  No tensor cores, no cuFFT.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <vector>
+
+#include "common_host.hpp"
+
+namespace pmr {
+
+struct WfParams {
+  const float2* res;       // resampler output ring
+  long long res_stride, res_mask;
+  long long r0;            // first sample of this chunk
+  long long ny;            // samples in this chunk
+  int W, nfft, hop;
+  int n_transforms;        // floor(ny / hop)
+  int parts;               // blocks per stream
+  const float* window;     // [W] scaled Hann
+  const float2* twiddle;   // [nfft] exp(-2 pi i k / nfft)
+  int n_stages;
+  int radix[16];
+  float* partial;          // [n_streams][parts][nfft]
+};
+
+template <int R>
+__device__ __forceinline__ void wf_stage(const float2* __restrict__ x, float2* __restrict__ y, const float2* __restrict__ tw, int N, int Ns) {
+  const int nb = N / R;
+  for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+    const int k = j % Ns;
+    float2 v[R];
+    const int tstep = N / (Ns * R);
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      float2 a = x[j + r * nb];
+      if (r > 0) {
+        const float2 w = tw[(r * k * tstep) % N];
+        a = make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+      }
+      v[r] = a;
+    }
+    const int j0 = (j - k) * R + k;
+    if (R == 2) {
+      y[j0] = make_float2(v[0].x + v[1].x, v[0].y + v[1].y);
+      y[j0 + Ns] = make_float2(v[0].x - v[1].x, v[0].y - v[1].y);
+    } else if (R == 4) {
+      // forward DFT: W4 = -i
+      const float2 s02 = make_float2(v[0].x + v[2].x, v[0].y + v[2].y), d02 = make_float2(v[0].x - v[2].x, v[0].y - v[2].y);
+      const float2 s13 = make_float2(v[1].x + v[3].x, v[1].y + v[3].y), d13 = make_float2(v[1].x - v[3].x, v[1].y - v[3].y);
+      y[j0] = make_float2(s02.x + s13.x, s02.y + s13.y);
+      y[j0 + Ns] = make_float2(d02.x + d13.y, d02.y - d13.x);      // d02 - i d13
+      y[j0 + 2 * Ns] = make_float2(s02.x - s13.x, s02.y - s13.y);
+      y[j0 + 3 * Ns] = make_float2(d02.x - d13.y, d02.y + d13.x);  // d02 + i d13
+    } else {
+      const int rstep = N / R;
+#pragma unroll
+      for (int q = 0; q < R; q++) {
+        float2 acc = v[0];
+#pragma unroll
+        for (int r = 1; r < R; r++) {
+          const float2 w = tw[((q * r) % R) * rstep];
+          acc.x += v[r].x * w.x - v[r].y * w.y;
+          acc.y += v[r].x * w.y + v[r].y * w.x;
+        }
+        y[j0 + q * Ns] = acc;
+      }
+    }
+  }
+}
+
+// generic prime radix p (reads straight from shared memory, O(p^2) per butterfly)
+__device__ __forceinline__ void wf_stage_generic(int R, const float2* __restrict__ x, float2* __restrict__ y, const float2* __restrict__ tw, int N, int Ns) {
+  const int nb = N / R, tstep = N / (Ns * R), rstep = N / R;
+  for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+    const int k = j % Ns;
+    const int j0 = (j - k) * R + k;
+    for (int q = 0; q < R; q++) {
+      float2 acc = x[j];
+      for (int r = 1; r < R; r++) {
+        float2 a = x[j + r * nb];
+        const float2 w1 = tw[(int)(((long long)r * k * tstep) % N)];
+        const float2 w2 = tw[((q * r) % R) * rstep];
+        const float2 w = make_float2(w1.x * w2.x - w1.y * w2.y, w1.x * w2.y + w1.y * w2.x);
+        acc.x += a.x * w.x - a.y * w.y;
+        acc.y += a.x * w.y + a.y * w.x;
+      }
+      y[j0 + q * Ns] = acc;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) wf_accumulate_kernel(WfParams p) {
+  extern __shared__ float2 wf_smem[];
+  float2* a = wf_smem;
+  float2* b = wf_smem + p.nfft;
+  float* acc = (float*)(wf_smem + 2 * p.nfft);
+  const int s = blockIdx.x / p.parts, part = blockIdx.x % p.parts;
+  const float2* res = p.res + (long long)s * p.res_stride;
+  for (int i = threadIdx.x; i < p.nfft; i += blockDim.x) acc[i] = 0.0f;
+  // transform t (1-based) fires after t*hop samples of the chunk and sees the last W of them
+  for (int t = 1 + part; t <= p.n_transforms; t += p.parts) {
+    __syncthreads();
+    const long long first = (long long)t * p.hop - p.W;  // chunk-local index of window sample 0
+    for (int i = threadIdx.x; i < p.nfft; i += blockDim.x) {
+      float2 v = make_float2(0.0f, 0.0f);
+      if (i < p.W) {
+        const long long li = first + i;
+        if (li >= 0) {
+          const float2 x = res[(p.r0 + li) & p.res_mask];
+          const float w = p.window[i];
+          v = make_float2(x.x * w, x.y * w);
+        }
+      }
+      a[i] = v;
+    }
+    __syncthreads();
+    float2 *x = a, *y = b;
+    int Ns = 1;
+    for (int st = 0; st < p.n_stages; st++) {
+      const int R = p.radix[st];
+      if (R == 4) wf_stage<4>(x, y, p.twiddle, p.nfft, Ns);
+      else if (R == 2) wf_stage<2>(x, y, p.twiddle, p.nfft, Ns);
+      else if (R == 3) wf_stage<3>(x, y, p.twiddle, p.nfft, Ns);
+      else if (R == 5) wf_stage<5>(x, y, p.twiddle, p.nfft, Ns);
+      else wf_stage_generic(R, x, y, p.twiddle, p.nfft, Ns);
+      Ns *= R;
+      float2* tmp = x; x = y; y = tmp;
+      __syncthreads();
+    }
+    for (int i = threadIdx.x; i < p.nfft; i += blockDim.x) acc[i] += x[i].x * x[i].x + x[i].y * x[i].y;
+  }
+  __syncthreads();
+  float* out = p.partial + ((long long)s * p.parts + part) * p.nfft;
+  for (int i = threadIdx.x; i < p.nfft; i += blockDim.x) out[i] = acc[i];
+}
+
+struct WfFinalParams {
+  const float* partial;
+  int parts, W, nfft, n_transforms;
+  float ref, div;
+  char* ascii;   // [n_streams][W]
+  float* peak;   // [n_streams][2]
+  float* psd;    // [n_streams][nfft]
+  float* scratch;  // [n_streams][nfft] dB values when psd == nullptr
+};
+
+__global__ void __launch_bounds__(256) wf_finalize_kernel(WfFinalParams p) {
+  const int s = blockIdx.x;
+  __shared__ float best_v[256];
+  __shared__ int best_i[256];
+  char* ascii = p.ascii ? p.ascii + (long long)s * p.W : nullptr;
+  if (p.n_transforms == 0) {  // asgramcf_execute with no transforms: blanks, peak 0
+    if (ascii) for (int i = threadIdx.x; i < p.W; i += blockDim.x) ascii[i] = ' ';
+    if (p.peak && threadIdx.x == 0) { p.peak[2 * s] = 0.0f; p.peak[2 * s + 1] = 0.0f; }
+    if (p.psd) for (int i = threadIdx.x; i < p.nfft; i += blockDim.x) p.psd[(long long)s * p.nfft + i] = 0.0f;
+    return;
+  }
+  float* db = (p.psd ? p.psd : p.scratch) + (long long)s * p.nfft;
+  const float scale = 1.0f / (float)p.n_transforms;
+  const int half = p.nfft / 2;
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < p.nfft; i += blockDim.x) {
+    const int k = (i + half) % p.nfft;
+    float a = 0.0f;
+    for (int q = 0; q < p.parts; q++) a += p.partial[((long long)s * p.parts + q) * p.nfft + k];
+    const float v = a > 1e-12f ? a : 1e-12f;
+    const float d = 10.0f * log10f(v * scale);
+    db[i] = d;
+    if (d > bv) { bv = d; bi = i; }
+  }
+  best_v[threadIdx.x] = bv;
+  best_i[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const float v2 = best_v[threadIdx.x + o];
+      const int i2 = best_i[threadIdx.x + o];
+      if (v2 > best_v[threadIdx.x] || (v2 == best_v[threadIdx.x] && i2 < best_i[threadIdx.x])) {
+        best_v[threadIdx.x] = v2;
+        best_i[threadIdx.x] = i2;
+      }
+    }
+    __syncthreads();
+  }
+  if (p.peak && threadIdx.x == 0) {
+    p.peak[2 * s] = best_v[0];
+    p.peak[2 * s + 1] = (float)best_i[0] / (float)p.nfft - 0.5f;
+  }
+  if (ascii) {
+    const char levelchar[11] = " .,-+*&NM#";
+    for (int i = threadIdx.x; i < p.W; i += blockDim.x) {
+      float val = db[4 * i];
+#pragma unroll
+      for (int j = 1; j < 4; j++) val = fmaxf(val, db[4 * i + j]);
+      char c = levelchar[0];
+      for (int j = 0; j < 10; j++)
+        if (val > p.ref + (float)j * p.div) c = levelchar[j];
+      ascii[i] = c;
+    }
+  }
+}
+
+struct Waterfall {
+  int S = 0;
+  unsigned W = 0, nfft = 0;
+  int parts = 1;
+  float ref = -40.0f, div = 2.0f;   // asgramcf_set_scale(-40, 2), src/sdr_pmr446.c:476
+  std::vector<int> radix;
+  DevBuf d_window, d_twiddle, d_partial, d_scratch;
+  size_t smem = 0;
+
+  int init(int n_streams, unsigned width) {
+    S = n_streams;
+    W = width;
+    nfft = 4 * width;
+    if (W < 2 || W > 2048) return fail(PMR446_EINVAL, "waterfall width must be in [2, 2048]");
+    unsigned n = nfft;
+    while (n % 4 == 0) { radix.push_back(4); n /= 4; }
+    for (unsigned pr = 2; n > 1;) {
+      if (n % pr == 0) { radix.push_back((int)pr); n /= pr; }
+      else pr++;
+    }
+    if (radix.size() > 16) return fail(PMR446_EINVAL, "waterfall width has too many prime factors");
+    for (int r : radix)
+      if (r > 61) return fail(PMR446_EINVAL, "waterfall width has a prime factor > 61");
+    std::vector<float> w = design::asgram_window(W);
+    std::vector<float2> tw(nfft);
+    for (unsigned k = 0; k < nfft; k++) {
+      double a = -2.0 * M_PI * (double)k / (double)nfft;
+      tw[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    parts = std::max(1, std::min(16, (296 + S - 1) / S));
+    int rc;
+    if ((rc = d_window.alloc(W * sizeof(float))) || (rc = d_twiddle.alloc(nfft * sizeof(float2))) ||
+        (rc = d_partial.alloc((size_t)S * parts * nfft * sizeof(float))) || (rc = d_scratch.alloc((size_t)S * nfft * sizeof(float))))
+      return rc;
+    CUDA_TRY(cudaMemcpy(d_window.p, w.data(), W * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_twiddle.p, tw.data(), nfft * sizeof(float2), cudaMemcpyHostToDevice));
+    smem = (size_t)nfft * (2 * sizeof(float2) + sizeof(float));
+    CUDA_TRY(cudaFuncSetAttribute(wf_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return 0;
+  }
+
+  int execute(const float2* res, long long res_cap, long long r0, long long ny, char* ascii, float* peak, float* psd, cudaStream_t st,
+              int* launches) {
+    WfParams p;
+    p.res = res;
+    p.res_stride = res_cap;
+    p.res_mask = res_cap - 1;
+    p.r0 = r0;
+    p.ny = ny;
+    p.W = (int)W;
+    p.nfft = (int)nfft;
+    p.hop = (int)(W / 2);
+    p.n_transforms = (int)(ny / p.hop);
+    p.parts = parts;
+    p.window = (const float*)d_window.p;
+    p.twiddle = (const float2*)d_twiddle.p;
+    p.n_stages = (int)radix.size();
+    for (size_t i = 0; i < radix.size(); i++) p.radix[i] = radix[i];
+    p.partial = (float*)d_partial.p;
+    if (p.n_transforms > 0) {
+      wf_accumulate_kernel<<<S * parts, 256, smem, st>>>(p);
+      (*launches)++;
+    }
+    WfFinalParams f;
+    f.partial = p.partial;
+    f.parts = parts;
+    f.W = p.W;
+    f.nfft = p.nfft;
+    f.n_transforms = p.n_transforms;
+    f.ref = ref;
+    f.div = div;
+    f.ascii = ascii;
+    f.peak = peak;
+    f.psd = psd;
+    f.scratch = (float*)d_scratch.p;
+    wf_finalize_kernel<<<S, 256, 0, st>>>(f);
+    (*launches)++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
+};
+
+}  // namespace pmr

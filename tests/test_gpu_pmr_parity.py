@@ -1,0 +1,142 @@
+"""GPU parity of the batched PMR446 chain against the CPU oracle (through the C ABI, host buffers).
+
+Tolerances are BASELINE.json's: float stage outputs (resampler, channelizer, discriminator, audio)
+within 1e-4 relative RMS of the oracle, s16 audio within +-1 LSB.  The relative RMS is taken
+ (a) over each whole stage output (all 16 channels together), and
+ (b) per signal-bearing channel.
+Empty channels only hold the receiver noise floor (about -32 dB below a carrier); there the
+oracle's OWN float32 rounding -- its DC blocker runs at |v| ~ 46 where one ulp is 3.8e-6 -- already
+sits at 0.9e-4 of the channel RMS (measured against a float64 DC blocker), so two
+correct float32 implementations cannot agree to 1e-4 of the noise floor.  For those channels the
+test asserts 5e-4 of the channel's own RMS and 1e-4 of the stage RMS.  The discriminator is
+ill-conditioned on noise-only channels and is compared on signal-bearing ones.
+"""
+import numpy as np
+import pytest
+
+from util import PCM_TOL_LSB, REL_RMS_TOL, active_channels, rel_rms
+
+pytestmark = pytest.mark.gpu
+
+EMPTY_CH_TOL = 5e-4
+
+
+def _run_pair(fs, n, chunk, fmt_cu8=True, streams=1, lowpass=0, gain=1.0, chunks_gpu=None, waterfall=0):
+    from oracle import oracle as orc
+    from sdr_pmr446_b200 import chain, synth
+    caps, carriers = [], []
+    for s in range(streams):
+        car = synth.rotated_carriers(s)
+        spec = synth.CaptureSpec(fs=float(fs), carriers=car)
+        caps.append(synth.make_cu8(spec, n, 446 + s) if fmt_cu8 else synth.make_cf32(spec, n, 446 + s))
+        carriers.append(car)
+    iq = np.stack(caps)
+    fmt = 1 if fmt_cu8 else 0
+    want = ("res", "chan", "demod", "lpcomp", "audio", "pcm") + (("ascii",) if waterfall else ())
+    gpu = chain.PmrBatch(n_streams=streams, fs_in=fs, in_fmt=fmt, audio_gain=gain, lowpass=lowpass, max_chunk=chunk,
+                         waterfall=waterfall)
+    g = gpu.run(iq, chunks_gpu or chunk, want)
+    gpu.close()
+    refs = []
+    for s in range(streams):
+        o = orc.PmrOracle(fs_in=fs, in_fmt=fmt, audio_gain=gain, lowpass=lowpass, chunk=chunk, waterfall=waterfall)
+        refs.append(o.run(iq[s], chunk))
+        o.close()
+    return g, refs, carriers
+
+
+def _check(g, refs, carriers):
+    for s, (r, car) in enumerate(zip(refs, carriers)):
+        assert g["ny"] == r["ny"] and g["ns"] == r["ns"], (g["ny"], r["ny"], g["ns"], r["ns"])
+        assert rel_rms(g["res"][s], r["res"]) < REL_RMS_TOL
+        assert rel_rms(g["chan"][s], r["chan"]) < REL_RMS_TOL
+        act = active_channels(car)
+        stage_rms = np.sqrt(np.mean(np.abs(r["chan"]) ** 2))
+        for c in range(16):
+            e = rel_rms(g["chan"][s, c], r["chan"][c])
+            if c in act:
+                assert e < REL_RMS_TOL, ("chan", s, c, e)
+            else:
+                ch_rms = np.sqrt(np.mean(np.abs(r["chan"][c]) ** 2))
+                assert e < EMPTY_CH_TOL and e * ch_rms / stage_rms < REL_RMS_TOL, ("empty chan", s, c, e)
+        for c in act:
+            # sample 0 is arg(conj(0) * x): sign-of-zero dependent in the reference itself; if it differs,
+            # skip the span of the audio FIRs behind it
+            sl = slice(1, None) if g["demod"][s, c, 0] == r["demod"][c, 0] else slice(500, None)
+            assert rel_rms(g["demod"][s, c, sl], r["demod"][c, sl]) < REL_RMS_TOL, ("demod", s, c)
+            assert rel_rms(g["audio"][s, c, sl], r["audio"][c, sl]) < REL_RMS_TOL, ("audio", s, c)
+            # the CTCSS branch is a difference of two nearly equal signals above 400 Hz: compare against the demod scale
+            d = g["lpcomp"][s, c, sl] - r["lpcomp"][c, sl]
+            assert np.sqrt(np.mean(d ** 2)) / np.sqrt(np.mean(r["demod"][c, sl] ** 2)) < REL_RMS_TOL, ("lpcomp", s, c)
+            dp = np.abs(g["pcm"][s, c, sl].astype(np.int32) - r["pcm"][c, sl].astype(np.int32))
+            assert dp.max() <= PCM_TOL_LSB, ("pcm", s, c, int(dp.max()))
+
+
+def test_cfg_a_1024k_cu8_single_stream():
+    """BASELINE config 1 (shortened): 1.024 Msps cu8, 100 000-sample chunks, 4 FM carriers + CTCSS."""
+    g, refs, car = _run_pair(1024000, 600000, 100000)
+    _check(g, refs, car)
+
+
+def test_cfg_b_2400k_cu8_three_streams():
+    """BASELINE config 3 (shortened): 2.4 Msps cu8 captures, rotated channel sets."""
+    g, refs, car = _run_pair(2400000, 720000, 240000, streams=3)
+    _check(g, refs, car)
+
+
+def test_cf32_input_and_lowpass():
+    g, refs, car = _run_pair(1024000, 300000, 100000, fmt_cu8=False, lowpass=1)
+    _check(g, refs, car)
+
+
+def test_chunk_invariance_odd_chunks():
+    """Chunked streaming with awkward chunk sizes equals the oracle's 100 000-sample chunking."""
+    g, refs, car = _run_pair(1024000, 300000, 100000, chunks_gpu=65537)
+    _check(g, refs, car)
+
+
+def test_tiny_chunks_and_empty_call():
+    """Chunks smaller than one channelizer frame / one half-band group, and n = 0."""
+    from oracle import oracle as orc
+    from sdr_pmr446_b200 import chain, synth
+    fs, n = 1024000, 40000
+    iq = synth.make_cu8(synth.CaptureSpec(fs=float(fs)), n, 446)
+    gpu = chain.PmrBatch(n_streams=1, fs_in=fs, in_fmt=1, audio_gain=1.0, max_chunk=100000)
+    sizes = [0, 1, 3, 16, 5, 777, 0, 10000, 64, 29134]
+    assert sum(sizes) == n
+    parts, o = [], 0
+    for k in sizes:
+        parts.append(gpu.execute(iq[None, 2 * o:2 * (o + k)]))
+        o += k
+    gpu.close()
+    g = {"ny": sum(p["ny"] for p in parts), "ns": sum(p["ns"] for p in parts)}
+    for k in ("res", "chan", "demod", "lpcomp", "audio", "pcm"):
+        g[k] = np.concatenate([p[k] for p in parts], axis=-1)
+    ref = orc.PmrOracle(fs_in=fs, in_fmt=1, audio_gain=1.0, chunk=100000)
+    r = ref.run(iq, 100000)
+    ref.close()
+    _check(g, [r], [synth.CFG1_CARRIERS])
+
+
+def test_waterfall_rows_match():
+    """asgram row per chunk (W = 120 -> 480-point, non-power-of-two FFT): dB values, peak and characters."""
+    g, refs, car = _run_pair(1024000, 300000, 100000, waterfall=120)
+    r = refs[0]
+    assert g["psd"].shape[1:] == r["psd"].shape
+    assert np.max(np.abs(g["psd"][0] - r["psd"])) < 0.02       # dB
+    assert np.max(np.abs(g["peak"][0] - r["peak"])) < 0.02
+    mism = np.sum(g["ascii"][0] != r["ascii"])                    # characters flip only at a 2 dB level edge
+    assert mism <= 2, mism
+
+
+def test_reset_restarts_the_stream():
+    from sdr_pmr446_b200 import chain, synth
+    iq = synth.make_cu8(synth.CaptureSpec(fs=1024000.0), 100000, 446)[None, :]
+    gpu = chain.PmrBatch(n_streams=1, fs_in=1024000, in_fmt=1, audio_gain=1.0, max_chunk=100000)
+    a = gpu.execute(iq)
+    gpu.execute(iq)
+    gpu.reset()
+    b = gpu.execute(iq)
+    gpu.close()
+    for k in ("res", "chan", "audio", "pcm"):
+        assert np.array_equal(a[k], b[k]), k

@@ -1,0 +1,283 @@
+"""Analytic known-answer tests that pin the CPU oracle (the reference ships no tests,
+golden vectors or fixtures, so these are the independent checks the restatement is held to).
+
+CPU only.  Each test cites the reference call site / SURVEY appendix item whose behaviour it pins.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+from scipy.signal import freqz
+from scipy.signal.windows import kaiser as scipy_kaiser
+
+from oracle import oracle as orc
+from sdr_pmr446_b200 import synth
+
+L = orc.lib()
+
+
+def _hp_taps():
+    # the table the reference passes to firfilt_rrrf_create (src/sdr_pmr446.c:56-104), via include/pmr446_taps.h
+    import re, os
+    txt = open(os.path.join(os.path.dirname(__file__), "..", "include", "pmr446_taps.h")).read()
+    m = re.search(r"pmr446_hp_audio_taps_half\[189\] = \{(.*?)\};", txt, re.S)
+    half = np.array([float(v.rstrip("f")) for v in re.findall(r"[-+]?\d+\.\d+f", m.group(1))], np.float32)
+    assert half.size == 189
+    return np.concatenate([half, half[-2::-1]])
+
+
+def test_kaiser_window_matches_scipy():
+    """A.6: liquid_kaiser(i, n, beta) = I0(beta sqrt(1 - r^2)) / I0(beta), r = 2t/(n-1)."""
+    n, beta = 417, float(L.kaiser_beta_As(80.0))
+    assert abs(beta - 0.1102 * (80 - 8.7)) < 1e-5
+    w = np.array([L.liquid_kaiser(i, n, beta) for i in range(n)])
+    assert np.max(np.abs(w - scipy_kaiser(n, beta))) < 2e-5
+
+
+@pytest.mark.parametrize("rate,stages,ms,step", [
+    (200000 / 1024000, 2, [10, 5], 21474836),          # PMR chain, src/sdr_pmr446.c:425-426
+    (200000 / 2400000, 3, [10, 5, 3], 25165824),       # BASELINE cfg 3/5
+    (12500 / 1024000, 6, [10, 5, 3, 3, 3, 3], 21474836),  # dsd_in, src/dsd_in.c:100
+    (12500 / 2400000, 7, [10, 5, 3, 3, 3, 3, 3], 25165824),
+])
+def test_msresamp_plan_constants(rate, stages, ms, step):
+    """A.2/A.3/A.5 and Appendix B: stage count, half-band semi-lengths, 24-bit phase step."""
+    q = L.msresamp_crcf_create(rate, 60.0)
+    st, m, ra, sp, npfb = C.c_uint(), (C.c_uint * 16)(), C.c_float(), C.c_uint(), C.c_uint()
+    L.oracle_msresamp_crcf_plan(q, C.byref(st), m, C.byref(ra), C.byref(sp), C.byref(npfb))
+    L.msresamp_crcf_destroy(q)
+    assert st.value == stages and list(m)[:stages] == ms and sp.value == step and npfb.value == 256
+
+
+def test_upsampler_step_uses_float32_division():
+    """Appendix B: 48k/12.5k -> arbitrary rate 1.92, step 8 738 134 (exact arithmetic would give ...133)."""
+    q = L.msresamp_rrrf_create(48000 / 12500, 60.0)
+    x = np.zeros(1000, np.float32)
+    y = np.zeros(4000, np.float32)
+    ny = C.c_uint()
+    L.msresamp_rrrf_execute(q, x.ctypes.data, 1000, y.ctypes.data, C.byref(ny))
+    L.msresamp_rrrf_destroy(q)
+    assert ny.value == 2 * -(-1000 * (1 << 24) // 8738134)
+
+
+def test_nco_frequency_word():
+    """A.7: the reference's offset -(15/32) 2 pi evaluates to exactly 0x88000000 (period-32 phasor)."""
+    q = L.nco_crcf_create(1)
+    L.nco_crcf_set_frequency(q, np.float32(-0.5 * 15 / 16 * 2 * np.pi))
+    assert L.oracle_nco_crcf_get_dtheta_u32(q) == 0x88000000
+    L.nco_crcf_destroy(q)
+
+
+def _channelize(x):
+    """NCO mix-down + firpfbch analyzer over a 200 kHz stream (loop body src/sdr_pmr446.c:804-823)."""
+    nco = L.nco_crcf_create(1)
+    L.nco_crcf_set_frequency(nco, np.float32(-0.5 * 15 / 16 * 2 * np.pi))
+    k = np.arange(x.size)
+    mixed = (x * np.exp(-2j * np.pi * ((k * 17) % 32) / 32)).astype(np.complex64)
+    ch = L.firpfbch_crcf_create_kaiser(0, 16, 13, 80.0)
+    nf = x.size // 16
+    out = np.zeros((nf, 16), np.complex64)
+    tmp = np.zeros(16, np.complex64)
+    for f in range(nf):
+        blk = np.ascontiguousarray(mixed[16 * f:16 * f + 16])
+        L.firpfbch_crcf_analyzer_execute(ch, blk.ctypes.data, tmp.ctypes.data)
+        out[f] = tmp
+    L.firpfbch_crcf_destroy(ch)
+    L.nco_crcf_destroy(nco)
+    return out.T
+
+
+@pytest.mark.parametrize("chan", [1, 5, 8, 16])
+def test_tone_lands_in_its_channel(chan):
+    """A.8: a tone at PMR channel k (1-based) -> bin k-1, gain ~16 (Sum h = 16.0005), others >= 70 dB down."""
+    n = 16 * 400
+    f = synth.channel_offset_hz(chan) / 200000.0
+    x = np.exp(2j * np.pi * f * np.arange(n)).astype(np.complex64)
+    y = _channelize(x)[:, 100:]
+    p = 10 * np.log10(np.mean(np.abs(y) ** 2, axis=1) + 1e-30)
+    assert np.argmax(p) == chan - 1
+    assert abs(p[chan - 1] - 20 * np.log10(16.0005)) < 0.05
+    others = np.delete(p, chan - 1)
+    assert others.max() < p[chan - 1] - 70
+
+
+def test_discriminator_scale():
+    """A.9: kf = 0.5 -> m = dphi / pi; a carrier offset of df Hz at 12.5 kHz reads df / 6250."""
+    fs, df = 12500.0, 2500.0
+    x = np.exp(2j * np.pi * df / fs * np.arange(2000)).astype(np.complex64)
+    q = L.freqdem_create(0.5)
+    m = np.zeros(2000, np.float32)
+    L.freqdem_demodulate_block(q, x.ctypes.data, 2000, m.ctypes.data)
+    L.freqdem_destroy(q)
+    assert m[0] == 0.0
+    assert np.max(np.abs(m[1:] - df / 6250.0)) < 1e-5
+
+
+def test_hp_fir_response_and_oracle_firfilt():
+    """8a row a8: <= -80 dB up to 300 Hz, about 0 dB from 400 Hz; oracle firfilt == direct convolution (A.10)."""
+    h = _hp_taps()
+    w, H = freqz(h, worN=8192, fs=12500.0)
+    mag = 20 * np.log10(np.abs(H) + 1e-12)
+    assert mag[w <= 300].max() < -79.0
+    assert np.all(np.abs(mag[(w >= 400) & (w <= 6000)]) < 0.3)
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(3000).astype(np.float32)
+    q = L.firfilt_rrrf_create(h.ctypes.data, h.size)
+    y = np.zeros_like(x)
+    xa, xb = x[:1000].copy(), x[1000:].copy()
+    L.firfilt_rrrf_execute_block(q, xa.ctypes.data, 1000, y.ctypes.data)
+    yy = np.zeros(2000, np.float32)
+    L.firfilt_rrrf_execute_block(q, xb.ctypes.data, 2000, yy.ctypes.data)   # state carries across calls
+    L.firfilt_rrrf_destroy(q)
+    ref = np.convolve(x.astype(np.float64), h.astype(np.float64))[:3000]
+    assert np.max(np.abs(np.concatenate([y[:1000], yy]) - ref)) < 1e-5
+
+
+def test_dc_blocker_corner():
+    """A.1: H(z) = (1 - z^-1)/(1 - 0.9995 z^-1): -3 dB at 81.5 Hz for 1.024 Msps, DC removed."""
+    fs = 1024000.0
+    n = 400000
+    t = np.arange(n)
+    q = L.iirfilt_crcf_create_dc_blocker(0.0005)
+    x = np.exp(2j * np.pi * 81.5 / fs * t).astype(np.complex64)
+    y = np.zeros_like(x)
+    L.iirfilt_crcf_execute_block(q, x.ctypes.data, n, y.ctypes.data)
+    L.iirfilt_crcf_destroy(q)
+    g = 20 * np.log10(np.sqrt(np.mean(np.abs(y[200000:]) ** 2)))
+    assert abs(g - (-3.0)) < 0.1
+    q = L.iirfilt_crcf_create_dc_blocker(0.0005)
+    x = np.full(n, 0.5 - 0.25j, np.complex64)
+    L.iirfilt_crcf_execute_block(q, x.ctypes.data, n, y.ctypes.data)
+    L.iirfilt_crcf_destroy(q)
+    assert abs(y[0] - x[0]) < 1e-7 and np.max(np.abs(y[100000:])) < 1e-5     # DC gone
+
+
+def test_deemphasis_corner():
+    """:461-463: 50 us de-emphasis, -3 dB at 3.18 kHz, unity at DC."""
+    b = np.array([0.507301437230636, 0.507301437230636], np.float32)
+    a = np.array([1.0, 0.014602874461272194], np.float32)
+    w, H = freqz(b, a, worN=[0.0, 3183.0], fs=12500.0)
+    assert abs(abs(H[0]) - 1.0) < 1e-3
+    assert abs(20 * np.log10(abs(H[1])) + 3.0) < 0.15
+    q = L.iirfilt_rrrf_create(b.ctypes.data, 2, a.ctypes.data, 2)
+    x = np.ones(100, np.float32)
+    y = np.zeros(100, np.float32)
+    L.iirfilt_rrrf_execute_block(q, x.ctypes.data, 100, y.ctypes.data)
+    L.iirfilt_rrrf_destroy(q)
+    assert abs(y[-1] - 1.0) < 1e-4 and abs(y[0] - b[0]) < 1e-7
+
+
+def test_resampler_gain_and_count():
+    """A.2-A.5: unity pass-band gain, output count = ceil(floor(n/4) * 2^24 / step) for the PMR plan."""
+    n = 40000
+    x = np.exp(2j * np.pi * 10000.0 / 1024000.0 * np.arange(n)).astype(np.complex64)
+    q = L.msresamp_crcf_create(200000 / 1024000, 60.0)
+    y = np.zeros(n, np.complex64)
+    ny = C.c_uint()
+    L.msresamp_crcf_execute(q, x.ctypes.data, n, y.ctypes.data, C.byref(ny))
+    L.msresamp_crcf_destroy(q)
+    assert ny.value == -(-(n // 4) * (1 << 24) // 21474836)
+    amp = np.abs(y[500:ny.value])
+    assert np.max(np.abs(amp - 1.0)) < 2e-3
+    ph = np.angle(y[501:ny.value] * np.conj(y[500:ny.value - 1]))
+    # 256 polyphase branches without interpolation: timing is quantised to 1/256 sample -> phase jitter 2 pi f/fs/256
+    assert np.max(np.abs(ph - 2 * np.pi * 10000.0 / 200000.0)) < 3e-3
+    assert abs(np.mean(ph) - 2 * np.pi * 10000.0 / 200000.0) < 2e-5
+
+
+def test_pmr_chain_end_to_end_tones():
+    """cfg1 (1 s): four FM carriers land in channels {2,7,8,15}; audio tones and discriminator amplitude 2500/6250."""
+    iq = synth.cfg1_capture(1024000)
+    o = orc.PmrOracle(in_fmt=1, audio_gain=1.0)
+    r = o.run(iq)
+    o.close()
+    assert r["ny"] == 200001 and r["ns"] == 12500
+    p = 10 * np.log10(np.mean(np.abs(r["chan"][:, 2000:]) ** 2, axis=1))
+    assert sorted(np.argsort(p)[-4:]) == [1, 6, 7, 14]
+    for ch, f in ((1, 1000.0), (6, 600.0), (7, 1700.0), (14, 2400.0)):
+        a = r["audio"][ch, 4000:]
+        sp = np.abs(np.fft.rfft(a * np.hanning(a.size)))
+        fr = np.fft.rfftfreq(a.size, 1 / 12500.0)
+        assert abs(fr[np.argmax(sp)] - f) < 2.0
+        # audio tone +-2.5 kHz -> 0.4 peak; CTCSS +-0.5 kHz adds 0.08 peak: total rms = sqrt(0.4^2 + 0.08^2)/sqrt(2)
+        # (the 2.4 kHz tone on channel 15 fills the 12.5 kHz channel and sits on the resampler's skirt: looser)
+        assert abs(r["demod"][ch, 4000:].std() - np.sqrt(0.4 ** 2 + 0.08 ** 2) / np.sqrt(2)) < (0.01 if ch != 14 else 0.03)
+        # the 377-tap high-pass removes the CTCSS tone: what is left is the audio tone through de-emphasis
+        assert np.array_equal(r["pcm"][ch], (r["audio"][ch] * np.float32(32767.0)).astype(np.int32).astype(np.int16))
+
+
+def test_lpcomp_is_the_ctcss_branch():
+    """A.11 / :884-890: wdelay(188) - highpass = complementary low-pass; it carries the CTCSS tone only."""
+    iq = synth.cfg1_capture(1024000)
+    o = orc.PmrOracle(in_fmt=1, audio_gain=1.0)
+    r = o.run(iq)
+    o.close()
+    a = r["lpcomp"][1, 4000:]
+    sp = np.abs(np.fft.rfft(a * np.hanning(a.size)))
+    fr = np.fft.rfftfreq(a.size, 1 / 12500.0)
+    assert abs(fr[np.argmax(sp)] - 67.0) < 2.0
+    assert abs(a.std() * np.sqrt(2) - 500.0 / 6250.0) < 0.01
+
+
+@pytest.mark.parametrize("chunk", [65536, 4099])
+def test_oracle_chunk_invariance(chunk):
+    """every object is stateful across calls, so chunking must not change the output."""
+    n = 250000
+    iq = synth.cfg1_capture(n)
+    a = orc.PmrOracle(in_fmt=1, audio_gain=1.0)
+    ra = a.run(iq, 100000)
+    a.close()
+    b = orc.PmrOracle(in_fmt=1, audio_gain=1.0)
+    rb = b.run(iq, chunk)
+    b.close()
+    assert ra["ny"] == rb["ny"] and ra["ns"] == rb["ns"]
+    for k in ("res", "chan", "demod", "audio", "pcm"):
+        assert np.array_equal(ra[k], rb[k]), k
+
+
+def test_dsd_chain_rates_and_tone():
+    """src/dsd_in.c:167-175: 1.024 Msps -> 12.5 kHz -> discriminator -> 48 kHz s16; tone survives, nz = 2*ceil(ny*2^24/step)."""
+    n = 1024000
+    spec = synth.CaptureSpec(fs=1024000.0, carriers=(synth.Carrier(1, 0.3, 1000.0, 0.0),), offset_hz=-synth.channel_offset_hz(1))
+    iq = synth.make_cu8(spec, n, 446)
+    o = orc.DsdOracle(in_fmt=1)
+    r = o.run(iq)
+    o.close()
+    assert r["ny"] == 12501 and r["nz"] == 2 * -(-r["ny"] * (1 << 24) // 8738134)
+    a = r["audio"][4000:]
+    sp = np.abs(np.fft.rfft(a * np.hanning(a.size)))
+    fr = np.fft.rfftfreq(a.size, 1 / 48000.0)
+    assert abs(fr[np.argmax(sp)] - 1000.0) < 2.0
+    assert abs(a.std() * np.sqrt(2) - 0.4) < 0.02
+
+
+def test_asgram_peak_and_row():
+    """A.13: a tone at +50 kHz of the 200 kHz stream peaks at f = 0.25 and lights the matching column."""
+    W = 120
+    q = L.asgramcf_create(W)
+    L.asgramcf_set_scale(q, -40.0, 2.0)
+    n = 19531
+    x = (0.5 * np.exp(2j * np.pi * 0.25 * np.arange(n))).astype(np.complex64)
+    L.asgramcf_write(q, x.ctypes.data, n)
+    row = np.zeros(W, np.uint8)
+    pv, pf = C.c_float(), C.c_float()
+    L.asgramcf_execute(q, row.ctypes.data, C.byref(pv), C.byref(pf))
+    assert abs(pf.value - 0.25) < 1.0 / (4 * W)
+    col = int(round((0.25 + 0.5) * W))
+    assert chr(row[col]) == "#" or chr(row[col - 1]) == "#"
+    assert chr(row[5]) == " "
+    # no samples since the last execute -> blanks and zero peak
+    L.asgramcf_execute(q, row.ctypes.data, C.byref(pv), C.byref(pf))
+    assert bytes(row) == b" " * W and pv.value == 0.0
+    L.asgramcf_destroy(q)
+
+
+def test_fft_matches_numpy():
+    """A.14: the oracle's mixed-radix FFT (16, 480, 6400 points) against numpy."""
+    rng = np.random.default_rng(3)
+    for n in (16, 480, 6400):
+        x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+        y = np.zeros(n, np.complex64)
+        L.oracle_fft_forward(n, x.ctypes.data, y.ctypes.data)
+        ref = np.fft.fft(x.astype(np.complex128))
+        assert np.max(np.abs(y - ref)) / np.max(np.abs(ref)) < 2e-6
