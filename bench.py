@@ -204,7 +204,6 @@ def run_ours(args, rank, world, local_rank):
         launches += batch.last_launches
     e1.record()
     barrier()
-    clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
     timings = batch.get_timings()
     batch.timing(False)
@@ -235,15 +234,15 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e_ns = ns.value
+    clocks = sampler.stop()   # sampled across both timed regions
 
     # ---------------- reduce over ranks ----------------
-    red = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    if distributed:
-        dist.all_reduce(red, op=dist.ReduceOp.MAX)
-        stats = torch.tensor([float(checksum)], dtype=torch.float64, device=dev)
-        gathered = [torch.zeros_like(stats) for _ in range(world)]
-        dist.all_gather(gathered, stats)   # NCCL is used for statistics only; the data path has no collective
-    ms_total, e2e_ms = float(red[0].item()), float(red[1].item())
+    # NCCL is used for statistics only; the data path has no collective (streams are independent)
+    from sdr_pmr446_b200 import shard
+    rank_stats = shard.gather_stats({"samples": float(S) * n * args.steps, "elapsed_ms": ms_total, "e2e_ms": e2e_s * 1e3,
+                                     "checksum": float(checksum % (1 << 40)), "sm_mhz": float(clocks.get("sm_mhz") or 0)}, device=dev)
+    ms_total = shard.max_over_ranks(ms_total, device=dev)
+    e2e_ms = shard.max_over_ranks(e2e_s * 1e3, device=dev)
     total_samples = float(world) * S * n * args.steps
     value = total_samples / (ms_total * 1e-3) / 1e6
     e2e_value = float(world) * S * n * e2e_steps / (e2e_ms * 1e-3) / 1e6
@@ -284,6 +283,7 @@ def run_ours(args, rank, world, local_rank):
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d host threads x 2 s of one 2.4 Msps stream each (all 16 channels demodulated), %.1f s wall" % (cores, cpu_dt)},
             "checksum": checksum,
+            "per_rank": rank_stats,
         }
         print(json.dumps(line), flush=True)
     batch.close()

@@ -250,6 +250,13 @@ int nco_crcf_step(nco_crcf q) {
   q->theta += q->d_theta;
   return LIQUID_OK;
 }
+int nco_crcf_mix_block_down(nco_crcf q, cf *x, cf *y, unsigned n) {
+  for (unsigned i = 0; i < n; i++) {
+    nco_crcf_mix_down(q, x[i], &y[i]);
+    nco_crcf_step(q);
+  }
+  return LIQUID_OK;
+}
 int nco_crcf_destroy(nco_crcf q) {
   free(q);
   return LIQUID_OK;

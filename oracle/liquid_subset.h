@@ -87,6 +87,7 @@ nco_crcf nco_crcf_create(liquid_ncotype type);
 int nco_crcf_set_frequency(nco_crcf q, float dtheta);
 int nco_crcf_mix_down(nco_crcf q, liquid_float_complex x, liquid_float_complex *y);
 int nco_crcf_step(nco_crcf q);
+int nco_crcf_mix_block_down(nco_crcf q, liquid_float_complex *x, liquid_float_complex *y, unsigned n);
 int nco_crcf_destroy(nco_crcf q);
 unsigned oracle_nco_crcf_get_dtheta_u32(nco_crcf q);
 

@@ -188,6 +188,11 @@ inline cascade_fn pick_cascade(int src, bool dc, bool arb, const int* ms, int* G
       if (is(3, 5, 0, 0)) return cfn<SRC_CF32, true, 16, 3, 5, 0, 0, false>();
       if (is(3, 3, 3, 3)) return cfn<SRC_CF32, true, 16, 3, 3, 3, 3, false>();
     }
+    if (!dc && src == SRC_CF32) {   // stand-alone msresamp_crcf (liquid shim): input is already DC-blocked
+      if (is(5, 0, 0, 0)) return cfn<SRC_CF32, false, 16, 5, 0, 0, 0, false>();
+      if (is(3, 5, 0, 0)) return cfn<SRC_CF32, false, 16, 3, 5, 0, 0, false>();
+      if (is(3, 3, 3, 3)) return cfn<SRC_CF32, false, 16, 3, 3, 3, 3, false>();
+    }
     if (!dc && src == SRC_RING) {
       if (is(5, 0, 0, 0)) return cfn<SRC_RING, false, 16, 5, 0, 0, 0, false>();
       if (is(3, 5, 0, 0)) return cfn<SRC_RING, false, 16, 3, 5, 0, 0, false>();
@@ -196,6 +201,7 @@ inline cascade_fn pick_cascade(int src, bool dc, bool arb, const int* ms, int* G
     if (!dc && src == SRC_RING && is(10, 0, 0, 0)) { *G = 8; return cfn<SRC_RING, false, 8, 10, 0, 0, 0, true>(); }
     if (dc && src == SRC_CU8 && is(0, 0, 0, 0)) return cfn<SRC_CU8, true, 16, 0, 0, 0, 0, true>();
     if (dc && src == SRC_CF32 && is(0, 0, 0, 0)) return cfn<SRC_CF32, true, 16, 0, 0, 0, 0, true>();
+    if (!dc && src == SRC_CF32 && is(0, 0, 0, 0)) return cfn<SRC_CF32, false, 16, 0, 0, 0, 0, true>();
   }
   return nullptr;
 }

@@ -11,7 +11,7 @@
 namespace pmr {
 
 // fm[n] = arg(conj(x[n-1]) x[n]) * ref, n in [n0, n1); x[-1] = 0
-__global__ void dsd_freqdem_kernel(const float2* res, long long res_stride, long long res_mask, float* fm, long long fm_stride, long long fm_mask,
+static __global__ void dsd_freqdem_kernel(const float2* res, long long res_stride, long long res_mask, float* fm, long long fm_stride, long long fm_mask,
                                    long long n0, long long n1, float ref) {
   const long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= n1) return;
@@ -27,7 +27,7 @@ __global__ void dsd_freqdem_kernel(const float2* res, long long res_stride, long
 
 // arbitrary resampler on a real ring (A.5): z[k] = sum_t pfb[idx_k][t] * fm[i_k - t],
 // i_k = floor(k*step / 2^24), idx_k = (k*step mod 2^24) >> (24 - bits)
-__global__ void dsd_arb_kernel(const float* fm, long long fm_stride, long long fm_mask, float* z, long long z_stride, long long z_mask,
+static __global__ void dsd_arb_kernel(const float* fm, long long fm_stride, long long fm_mask, float* z, long long z_stride, long long z_mask,
                                long long k0, long long k1, unsigned step, int bits, const float* pfb) {
   const long long k = k0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= k1) return;
@@ -58,7 +58,7 @@ struct DsdInterpParams {
   short* pcm;        // optional [n_streams][out_ld]
   long long out_ld;
 };
-__global__ void dsd_interp_kernel(DsdInterpParams p) {
+static __global__ void dsd_interp_kernel(DsdInterpParams p) {
   const long long k = p.k0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= p.k1) return;
   const int s = blockIdx.y;

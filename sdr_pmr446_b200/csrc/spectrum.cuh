@@ -99,7 +99,7 @@ __device__ __forceinline__ void wf_stage_generic(int R, const float2* __restrict
   }
 }
 
-__global__ void __launch_bounds__(256) wf_accumulate_kernel(WfParams p) {
+static __global__ void __launch_bounds__(256) wf_accumulate_kernel(WfParams p) {
   extern __shared__ float2 wf_smem[];
   float2* a = wf_smem;
   float2* b = wf_smem + p.nfft;
@@ -154,7 +154,7 @@ struct WfFinalParams {
   float* scratch;  // [n_streams][nfft] dB values when psd == nullptr
 };
 
-__global__ void __launch_bounds__(256) wf_finalize_kernel(WfFinalParams p) {
+static __global__ void __launch_bounds__(256) wf_finalize_kernel(WfFinalParams p) {
   const int s = blockIdx.x;
   __shared__ float best_v[256];
   __shared__ int best_i[256];
