@@ -161,6 +161,10 @@ extern "C" int dsd446_batch_execute(dsd446_batch* b, const void* iq, long long i
   const long long in_row = (long long)((b->cfg.max_chunk * bps + 63) / 64 * 64);
   int rc;
   if ((rc = b->d_in.ensure((size_t)S * in_row))) return rc;
+  if (iq_stride < (long long)(n * bps)) {   // a single stream may pass stride 0
+    if (S > 1) return fail(PMR446_EINVAL, "iq_stride smaller than one stream's chunk");
+    iq_stride = (long long)(n * bps);
+  }
   if (n) CUDA_TRY(cudaMemcpy2DAsync(b->d_in.p, in_row, iq, iq_stride, (size_t)n * bps, S, cudaMemcpyHostToDevice, st));
   dsd446_outputs d = *out;
   d.res_ld = b->max_res;

@@ -71,7 +71,7 @@ def reference_loop(L, iq_cf32, hp, lp, active_chan, chunk=100000, audio_gain=1.0
     assert all([dcblock, resampler, nco, channelizer, fm_demod, ctcss_filt, delay, audio_filt, deemph, ring])
     res_all, chan_all, audio_all, rows = [], [], [], []
     for o in range(0, iq_cf32.size, chunk):
-        buffp = np.ascontiguousarray(iq_cf32[o:o + chunk])
+        buffp = iq_cf32[o:o + chunk].copy()   # the DC blocker runs in place (:795): never touch the caller's capture
         n = buffp.size
         resamp_buf = np.zeros(39064, np.complex64)
         ny = C.c_uint()
