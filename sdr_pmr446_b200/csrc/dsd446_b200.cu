@@ -10,6 +10,7 @@
 
 #include "../../include/pmr446_b200.h"
 #include "common_host.hpp"
+#include "frontend_host.hpp"
 #include "design.hpp"
 #include "dsd.cuh"
 

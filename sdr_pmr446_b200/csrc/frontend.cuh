@@ -7,11 +7,20 @@
 // runs the cascade over it sample-group by sample-group with all filter windows in registers,
 // exactly like the CPU does for a whole stream -- but ~10^5-10^6 segments run concurrently.
 // A segment starts H samples early (zero state) so that its owned outputs only depend on real
-// samples (the cascade is FIR); the one IIR element, the DC blocker, gets its exact state at
-// the segment start from a two-level linear-recurrence scan (dc_local_kernel + dc_scan_kernel).
-// Taps are compile-time-indexed constant-bank operands of the FFMAs; no shared memory is used.
-// Lanes of a warp read 32-byte (cu8) / 128-byte (cf32) pieces of different segments, i.e. whole
-// DRAM sectors / lines, which L1/L2 turn into fully used transactions.
+// samples (the cascade is FIR).  Taps are compile-time-indexed constant-bank operands of the
+// FFMAs; no shared memory is used.  Lanes of a warp read 32-byte (cu8) / 64-128-byte (cf32)
+// pieces of different segments, i.e. whole DRAM sectors, and the next group's raw data is
+// fetched into registers one iteration ahead so the load latency hides behind ~400 FFMAs.
+// All per-iteration index arithmetic is 32-bit and relative to the segment start.
+//
+// The one IIR element, the DC blocker v[n] = x[n] + c v[n-1], y = v[n] - v[n-1], is linear, so
+// a segment's output is (zero-state response to its own samples) + (zero-input response to the
+// state V0 at its warm-up start).  DC_ZSR mode computes the zero-state part with no dependence
+// on other segments and records the segment's local sum; dc_scan_kernel chains the sums into
+// V0 per segment; the zero-input part, -alpha V0 E[k] with E = (cascade applied to c^i) a fixed
+// table that is exactly geometric past the warm-up, is added by the NEXT launch while it loads
+// the ring (Correction).  DC_SCAN mode (used when there is no next launch) gets V0 up front from
+// dc_local_kernel + dc_scan_kernel.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -19,6 +28,20 @@
 namespace pmr {
 
 enum { SRC_CU8 = 0, SRC_CF32 = 1, SRC_RING = 2 };
+enum { DC_NONE = 0, DC_SCAN = 1, DC_ZSR = 2 };
+
+// Zero-input-response correction applied while loading a ring written by a DC_ZSR launch.
+struct Correction {
+  const float2* v_seg;   // [n_streams][nseg] V0 of the producer's segments; nullptr = off
+  const float* e;        // [(halo + seg_len) / D] response of the producer's cascade to c^i
+  long long from;        // ring samples with index >= from still need the correction
+  long long seg0_out;    // producer's seg0 / D (ring index of segment 0's first owned output)
+  int seg_shift;         // log2(producer seg_len / D)
+  int halo_out;          // producer halo / D
+  int nseg;
+  float alpha;
+  float rho_pow[16];     // (c^D)^i: E[k + i] = E[k] rho^i for k >= halo_out
+};
 
 // Per-launch view of the input signal of all streams.
 //  two-source (SRC_CU8 / SRC_CF32): samples [hist_base, n0) live in `hist`, [n0, n1) in `cur`.
@@ -32,6 +55,7 @@ struct SrcView {
   long long n0, n1;       // new samples are [n0, n1)
   long long ring_mask;
   int cur_aligned;        // n0 % 16 == 0 and cur/cur_stride 16-byte aligned (two-source only)
+  Correction corr;
 };
 
 struct CascadeParams {
@@ -45,7 +69,9 @@ struct CascadeParams {
   float scale;            // 2^-NST, folded into the last stage's outputs
   // DC blocker
   float alpha;
-  const float2* v_seg;    // [n_streams][nseg] V at (segment start - halo)
+  const float2* v_seg;    // DC_SCAN: [n_streams][nseg] V at (segment start - halo)
+  float2* sums;           // DC_ZSR: [n_streams][nseg] local sums out
+  long long dc_end;       // DC_ZSR: sums stop at this absolute index (next chunk's P_0)
   // arbitrary resampler
   unsigned step;
   int bits;
@@ -59,41 +85,57 @@ struct CascadeParams {
   float hb[4][20];
 };
 
+// A group of G raw samples held in registers between fetch (issue the loads) and convert.
+template <int SRC, int G>
+struct Raw;
+template <int G>
+struct Raw<SRC_CU8, G> { uint4 v[G / 8]; };
+template <int G>
+struct Raw<SRC_CF32, G> { float4 v[G / 2]; };
+template <int G>
+struct Raw<SRC_RING, G> { float4 v[G / 2]; };
+
+// Per-thread loader state: `fast` means every group of the thread's range can be read with aligned
+// vector loads from one place, so fetch() is a pointer bump; otherwise each sample is guarded.
 template <int SRC>
 struct Loader;
 
-// ---- cu8 two-source --------------------------------------------------------------------
 __device__ __forceinline__ float u8f(unsigned w, int k) { return (float)((w >> (8 * k)) & 0xffu); }
 
+// ---- cu8 two-source --------------------------------------------------------------------
 template <>
 struct Loader<SRC_CU8> {
-  // loads G samples starting at absolute q (multiple of G) of stream s, converts with the
-  // SoapyRTLSDR rule (u8 - 127.4)/128
+  const uint8_t* hist;
+  const uint8_t* cur;
+  const uint4* fp;
+  int fast_lo, fast_hi;   // iterations [fast_lo, fast_hi) read whole aligned groups of the current chunk
   template <int G>
-  static __device__ __forceinline__ void load(const SrcView& v, int s, long long q, float* xr, float* xi) {
+  __device__ __forceinline__ void init(const SrcView& v, int s, long long qb) {
+    hist = (const uint8_t*)v.hist + (long long)s * v.hist_stride;
+    cur = (const uint8_t*)v.cur + (long long)s * v.cur_stride;
+    fast_lo = fast_hi = 0;
+    if (v.cur_aligned) {
+      const long long lo = (v.n0 - qb + G - 1) / G, hi = (v.n1 - qb) / G;
+      fast_lo = (int)(lo < 0 ? 0 : (lo > (1 << 30) ? (1 << 30) : lo));
+      fast_hi = (int)(hi < 0 ? 0 : (hi > (1 << 30) ? (1 << 30) : hi));
+    }
+    fp = (const uint4*)(cur + 2 * (qb - v.n0));
+  }
+  template <int G>
+  __device__ __forceinline__ void fetch(int it, Raw<SRC_CU8, G>& r) const {
+    if (it >= fast_lo && it < fast_hi) {
+#pragma unroll
+      for (int i = 0; i < G / 8; i++) r.v[i] = __ldg(fp + it * (G / 8) + i);
+    }
+  }
+  // converts with the SoapyRTLSDR rule (u8 - 127.4)/128
+  template <int G>
+  __device__ __forceinline__ void convert(const SrcView& v, long long q, int it, const Raw<SRC_CU8, G>& r, float* xr, float* xi) const {
     const float k = 1.0f / 128.0f, c0 = -127.4f / 128.0f;
-    const uint8_t* hist = (const uint8_t*)v.hist + (long long)s * v.hist_stride;
-    const uint8_t* cur = (const uint8_t*)v.cur + (long long)s * v.cur_stride;
-    if (q >= v.n0 && q + G <= v.n1 && v.cur_aligned) {
-      const uint4* p = (const uint4*)(cur + 2 * (q - v.n0));
+    if (it >= fast_lo && it < fast_hi) {
 #pragma unroll
       for (int i = 0; i < G / 8; i++) {
-        uint4 w = __ldg(p + i);
-        unsigned ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          xr[i * 8 + 2 * j] = fmaf(u8f(ww[j], 0), k, c0);
-          xi[i * 8 + 2 * j] = fmaf(u8f(ww[j], 1), k, c0);
-          xr[i * 8 + 2 * j + 1] = fmaf(u8f(ww[j], 2), k, c0);
-          xi[i * 8 + 2 * j + 1] = fmaf(u8f(ww[j], 3), k, c0);
-        }
-      }
-    } else if (q + G <= v.n0 && q >= v.hist_base) {
-      const uint4* p = (const uint4*)(hist + 2 * (q - v.hist_base));
-#pragma unroll
-      for (int i = 0; i < G / 8; i++) {
-        uint4 w = p[i];
-        unsigned ww[4] = {w.x, w.y, w.z, w.w};
+        const unsigned ww[4] = {r.v[i].x, r.v[i].y, r.v[i].z, r.v[i].w};
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           xr[i * 8 + 2 * j] = fmaf(u8f(ww[j], 0), k, c0);
@@ -105,14 +147,14 @@ struct Loader<SRC_CU8> {
     } else {
 #pragma unroll
       for (int i = 0; i < G; i++) {  // static indices keep xr/xi in registers
-        long long n = q + i;
-        float r = 0.0f, im = 0.0f;
+        const long long n = q + i;
+        float re = 0.0f, im = 0.0f;
         if (n >= 0 && n < v.n1 && (n >= v.n0 || n >= v.hist_base)) {
           const uint8_t* b = (n >= v.n0) ? cur + 2 * (n - v.n0) : hist + 2 * (n - v.hist_base);
-          r = fmaf((float)b[0], k, c0);
+          re = fmaf((float)b[0], k, c0);
           im = fmaf((float)b[1], k, c0);
         }
-        xr[i] = r;
+        xr[i] = re;
         xi[i] = im;
       }
     }
@@ -122,28 +164,40 @@ struct Loader<SRC_CU8> {
 // ---- cf32 two-source -------------------------------------------------------------------
 template <>
 struct Loader<SRC_CF32> {
+  const float2* hist;
+  const float2* cur;
+  const float4* fp;
+  int fast_lo, fast_hi;
   template <int G>
-  static __device__ __forceinline__ void load(const SrcView& v, int s, long long q, float* xr, float* xi) {
-    const float2* hist = (const float2*)((const char*)v.hist + (long long)s * v.hist_stride);
-    const float2* cur = (const float2*)((const char*)v.cur + (long long)s * v.cur_stride);
-    if (q >= v.n0 && q + G <= v.n1 && v.cur_aligned) {
-      const float4* p = (const float4*)(cur + (q - v.n0));
+  __device__ __forceinline__ void init(const SrcView& v, int s, long long qb) {
+    hist = (const float2*)((const char*)v.hist + (long long)s * v.hist_stride);
+    cur = (const float2*)((const char*)v.cur + (long long)s * v.cur_stride);
+    fast_lo = fast_hi = 0;
+    if (v.cur_aligned) {
+      const long long lo = (v.n0 - qb + G - 1) / G, hi = (v.n1 - qb) / G;
+      fast_lo = (int)(lo < 0 ? 0 : (lo > (1 << 30) ? (1 << 30) : lo));
+      fast_hi = (int)(hi < 0 ? 0 : (hi > (1 << 30) ? (1 << 30) : hi));
+    }
+    fp = (const float4*)(cur + (qb - v.n0));
+  }
+  template <int G>
+  __device__ __forceinline__ void fetch(int it, Raw<SRC_CF32, G>& r) const {
+    if (it >= fast_lo && it < fast_hi) {
+#pragma unroll
+      for (int i = 0; i < G / 2; i++) r.v[i] = __ldg(fp + it * (G / 2) + i);
+    }
+  }
+  template <int G>
+  __device__ __forceinline__ void convert(const SrcView& v, long long q, int it, const Raw<SRC_CF32, G>& r, float* xr, float* xi) const {
+    if (it >= fast_lo && it < fast_hi) {
 #pragma unroll
       for (int i = 0; i < G / 2; i++) {
-        float4 w = __ldg(p + i);
-        xr[2 * i] = w.x; xi[2 * i] = w.y; xr[2 * i + 1] = w.z; xi[2 * i + 1] = w.w;
-      }
-    } else if (q + G <= v.n0 && q >= v.hist_base) {
-      const float4* p = (const float4*)(hist + (q - v.hist_base));
-#pragma unroll
-      for (int i = 0; i < G / 2; i++) {
-        float4 w = p[i];
-        xr[2 * i] = w.x; xi[2 * i] = w.y; xr[2 * i + 1] = w.z; xi[2 * i + 1] = w.w;
+        xr[2 * i] = r.v[i].x; xi[2 * i] = r.v[i].y; xr[2 * i + 1] = r.v[i].z; xi[2 * i + 1] = r.v[i].w;
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < G; i++) {  // static indices keep xr/xi in registers
-        long long n = q + i;
+      for (int i = 0; i < G; i++) {
+        const long long n = q + i;
         float2 w = make_float2(0.0f, 0.0f);
         if (n >= 0 && n < v.n1) {
           if (n >= v.n0) w = cur[n - v.n0];
@@ -156,27 +210,72 @@ struct Loader<SRC_CF32> {
   }
 };
 
-// ---- cf32 ring (library-owned intermediate) -----------------------------------------------
+// ---- cf32 ring (library-owned intermediate), with the optional zero-input-response correction ----
 template <>
 struct Loader<SRC_RING> {
+  const float2* ring;
+  unsigned q32, mask32;
+  int fast_hi;            // iterations [0, fast_hi) read whole groups below n1
+  // correction state
+  const float2* vrow;     // producer V0 row of this stream, nullptr = off
+  int relc, from_rel;     // (q_begin - seg0_out), (from - seg0_out)
   template <int G>
-  static __device__ __forceinline__ void load(const SrcView& v, int s, long long q, float* xr, float* xi) {
-    const float2* ring = (const float2*)((const char*)v.cur + (long long)s * v.cur_stride);
-    if (q >= 0 && q + G <= v.n1) {
-      const float4* p = (const float4*)(ring + (q & v.ring_mask));
+  __device__ __forceinline__ void init(const SrcView& v, int s, long long qb) {
+    ring = (const float2*)((const char*)v.cur + (long long)s * v.cur_stride);
+    q32 = (unsigned)qb;
+    mask32 = (unsigned)v.ring_mask;
+    const long long hi = qb >= 0 ? (v.n1 - qb) / G : 0;
+    fast_hi = (int)(hi < 0 ? 0 : (hi > (1 << 30) ? (1 << 30) : hi));
+    vrow = v.corr.v_seg ? v.corr.v_seg + (long long)s * v.corr.nseg : nullptr;
+    const long long r = qb - v.corr.seg0_out, f = v.corr.from - v.corr.seg0_out;
+    relc = (int)(r < -(1 << 30) ? -(1 << 30) : r);
+    from_rel = (int)(f > (1 << 30) ? (1 << 30) : f);
+  }
+  template <int G>
+  __device__ __forceinline__ void fetch(int it, Raw<SRC_RING, G>& r) const {
+    if (it < fast_hi) {
+      const float4* p = (const float4*)(ring + ((q32 + (unsigned)(it * G)) & mask32));
+#pragma unroll
+      for (int i = 0; i < G / 2; i++) r.v[i] = p[i];
+    }
+  }
+  template <int G>
+  __device__ __forceinline__ void convert(const SrcView& v, long long q, int it, const Raw<SRC_RING, G>& r, float* xr, float* xi) const {
+    if (it < fast_hi) {
 #pragma unroll
       for (int i = 0; i < G / 2; i++) {
-        float4 w = p[i];
-        xr[2 * i] = w.x; xi[2 * i] = w.y; xr[2 * i + 1] = w.z; xi[2 * i + 1] = w.w;
+        xr[2 * i] = r.v[i].x; xi[2 * i] = r.v[i].y; xr[2 * i + 1] = r.v[i].z; xi[2 * i + 1] = r.v[i].w;
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < G; i++) {  // static indices keep xr/xi in registers
-        long long n = q + i;
+      for (int i = 0; i < G; i++) {
+        const long long n = q + i;
         float2 w = make_float2(0.0f, 0.0f);
-        if (n >= 0 && n < v.n1) w = ring[n & v.ring_mask];
+        if (n >= 0 && n < v.n1) w = ring[(unsigned)n & mask32];
         xr[i] = w.x;
         xi[i] = w.y;
+      }
+    }
+    // zero-input response of the producer's DC blocker: x -= alpha V0[seg] E[k].  The producer's
+    // segment grid is aligned to 16 ring samples, so a group never straddles two segments, and
+    // E[k0 + i] = E[k0] rho^i because every corrected sample lies past the producer's warm-up.
+    if (vrow) {
+      const int rel = relc + it * G;
+      if (rel + G > from_rel && rel >= 0) {
+        const Correction& c = v.corr;
+        const int t = rel >> c.seg_shift;
+        if (t < c.nseg) {
+          const float2 v0 = vrow[t];
+          const float e0 = __ldg(c.e + (rel - (t << c.seg_shift)) + c.halo_out);
+          const float ar = -c.alpha * v0.x * e0, ai = -c.alpha * v0.y * e0;
+#pragma unroll
+          for (int i = 0; i < G; i++) {
+            if (rel + i >= from_rel) {
+              xr[i] = fmaf(ar, c.rho_pow[i], xr[i]);
+              xi[i] = fmaf(ai, c.rho_pow[i], xi[i]);
+            }
+          }
+        }
       }
     }
   }
@@ -229,6 +328,7 @@ struct HbStage<0, B, STAGE> {  // absent stage
 };
 
 // ---- DC blocker local sums: S_t = sum_j c^(len-1-j) x[P_t + j] over segment t (A.1) -------
+// (only used in DC_SCAN mode, i.e. single-launch plans)
 struct DcLocalParams {
   SrcView src;
   int n_streams, nseg;
@@ -249,17 +349,17 @@ __global__ void __launch_bounds__(128) dc_local_kernel(DcLocalParams p) {
   if (b > p.end) b = p.end;
   float sr = 0.0f, si = 0.0f;
   if (a < 0) a = 0;  // P_0 and seg_len are multiples of 16, so a stays group-aligned
-  for (long long q = a; q < b; q += 16) {
+  Loader<SRC> ld;
+  ld.template init<16>(p.src, s, a);
+  int it = 0;
+  for (long long q = a; q < b; q += 16, it++) {
     float xr[16], xi[16];
-    Loader<SRC>::template load<16>(p.src, s, q, xr, xi);
-    if (q + 16 <= b) {
+    Raw<SRC, 16> raw;
+    ld.template fetch<16>(it, raw);
+    ld.template convert<16>(p.src, q, it, raw, xr, xi);
 #pragma unroll
-      for (int i = 0; i < 16; i++) { sr = fmaf(p.c, sr, xr[i]); si = fmaf(p.c, si, xi[i]); }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; i++)
-        if (q + i < b) { sr = fmaf(p.c, sr, xr[i]); si = fmaf(p.c, si, xi[i]); }
-    }
+    for (int i = 0; i < 16; i++)
+      if (q + i < b) { sr = fmaf(p.c, sr, xr[i]); si = fmaf(p.c, si, xi[i]); }
   }
   p.sums[gid] = make_float2(sr, si);
 }
@@ -273,29 +373,74 @@ struct DcScanParams {
   int seg_len;
   float c, decay_full;  // 1 - alpha and c^seg_len
 };
-static __global__ void dc_scan_kernel(DcScanParams p) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per stream: lanes take 32 consecutive segments, a shuffle scan composes the affine maps
+// V -> d V + s (d = c^len), the carry moves to the next 32 segments.
+static __global__ void __launch_bounds__(128) dc_scan_kernel(DcScanParams p) {
+  const int s = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
   if (s >= p.n_streams) return;
-  float2 v = p.v_lag[s];
-  for (int t = 0; t < p.nseg; t++) {
-    p.v_seg[(long long)s * p.nseg + t] = v;
-    long long a = p.p0 + (long long)t * p.seg_len, b = a + p.seg_len;
-    if (b > p.end) b = p.end;
-    if (a < 0) a = 0;
-    const long long len = b - a;
-    if (len <= 0) continue;
-    const float d = (len == p.seg_len) ? p.decay_full : powf(p.c, (float)len);
-    float2 sm = p.sums[(long long)s * p.nseg + t];
-    v.x = fmaf(d, v.x, sm.x);
-    v.y = fmaf(d, v.y, sm.y);
+  float2 carry = p.v_lag[s];
+  for (int base = 0; base < p.nseg; base += 32) {
+    const int t = base + lane;
+    float d = 1.0f;
+    float2 sm = make_float2(0.0f, 0.0f);
+    if (t < p.nseg) {
+      long long a = p.p0 + (long long)t * p.seg_len, b = a + p.seg_len;
+      if (b > p.end) b = p.end;
+      if (a < 0) a = 0;
+      const long long len = b - a;
+      if (len > 0) {
+        d = (len == p.seg_len) ? p.decay_full : powf(p.c, (float)len);
+        sm = p.sums[(long long)s * p.nseg + t];
+      }
+    }
+    // inclusive scan of (d, sm): (d2, s2) o (d1, s1) = (d1 d2, d2 s1 + s2)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float dp = __shfl_up_sync(0xffffffffu, d, o);
+      const float sx = __shfl_up_sync(0xffffffffu, sm.x, o), sy = __shfl_up_sync(0xffffffffu, sm.y, o);
+      if (lane >= o) {
+        sm.x = fmaf(d, sx, sm.x);
+        sm.y = fmaf(d, sy, sm.y);
+        d *= dp;
+      }
+    }
+    // V after segment t = d * carry + sm ; V before segment t = that of lane - 1 (or the carry)
+    float2 after = make_float2(fmaf(d, carry.x, sm.x), fmaf(d, carry.y, sm.y));
+    float bx = __shfl_up_sync(0xffffffffu, after.x, 1), by = __shfl_up_sync(0xffffffffu, after.y, 1);
+    if (lane == 0) { bx = carry.x; by = carry.y; }
+    if (t < p.nseg) p.v_seg[(long long)s * p.nseg + t] = make_float2(bx, by);
+    carry.x = __shfl_sync(0xffffffffu, after.x, 31);
+    carry.y = __shfl_sync(0xffffffffu, after.y, 31);
   }
-  p.v_lag[s] = v;
+  if (lane == 0) p.v_lag[s] = carry;
+}
+
+// in-place zero-input-response correction of the last `count` samples of a ring (they are the
+// next chunk's history, which the next launch reads as already corrected)
+static __global__ void zir_tail_kernel(float2* ring, long long ring_stride, long long ring_mask, Correction c, long long start, int count) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const int s = blockIdx.y;
+  const long long n = start + k;
+  if (n < c.from) return;
+  const long long rel = n - c.seg0_out;
+  if (rel < 0) return;
+  const int t = (int)(rel >> c.seg_shift);
+  if (t >= c.nseg) return;
+  const float2 v0 = c.v_seg[(long long)s * c.nseg + t];
+  const float e = c.e[(int)(rel - ((long long)t << c.seg_shift)) + c.halo_out];
+  float2* p = ring + (long long)s * ring_stride + (n & ring_mask);
+  float2 x = *p;
+  x.x = fmaf(-c.alpha * v0.x, e, x.x);
+  x.y = fmaf(-c.alpha * v0.y, e, x.y);
+  *p = x;
 }
 
 // ---- the cascade kernel ----------------------------------------------------------------------
 // Stage list MA,MB,MC,MD = semi-lengths in execution order (highest rate first), 0 = absent.
 // G = input samples per loop iteration (multiple of 2^NST).
-template <int SRC, bool DC, int G, int MA, int MB, int MC, int MD, bool ARB>
+template <int SRC, int DC, int G, int MA, int MB, int MC, int MD, bool ARB>
 __global__ void __launch_bounds__(128) cascade_kernel(CascadeParams p) {
   constexpr int NST = (MA > 0) + (MB > 0) + (MC > 0) + (MD > 0);
   constexpr int D = 1 << NST;
@@ -307,7 +452,29 @@ __global__ void __launch_bounds__(128) cascade_kernel(CascadeParams p) {
   long long i_lo = T0 / D, i_hi = (T0 + p.seg_len) / D;
   if (i_lo < p.out0) i_lo = p.out0;
   if (i_hi > p.out1) i_hi = p.out1;
-  if (i_hi <= i_lo) return;
+  long long qb = T0 - p.halo;
+  // DC_ZSR: where this segment's local sum is complete (the next segment's warm-up start)
+  long long q_cap = qb + p.seg_len;
+  if (DC == DC_ZSR && q_cap > p.dc_end) q_cap = p.dc_end;
+
+  float vr = 0.0f, vi = 0.0f;
+  if (DC == DC_SCAN && qb > 0) {
+    float2 v0 = p.v_seg[gid];
+    vr = v0.x; vi = v0.y;
+  }
+  if (qb < 0) qb = 0;
+  long long q_end = i_hi > i_lo ? i_hi * D : qb;
+  if (DC == DC_ZSR && q_cap > q_end) q_end = q_cap;
+  if (q_end <= qb) {
+    if (DC == DC_ZSR) p.sums[gid] = make_float2(0.0f, 0.0f);
+    return;
+  }
+  // everything below is 32-bit and relative to qb (a multiple of G and D)
+  const int n_it = (int)((q_end - qb + G - 1) / G);
+  const int cap_it = (DC == DC_ZSR) ? (q_cap > qb ? (int)((q_cap - qb) / G) : 0) : -1;   // q_cap is a multiple of G
+  const long long ob = qb / D;                                          // absolute index of local output 0
+  int own_lo = (int)(i_lo - ob), own_hi = (int)(i_hi - ob);             // owned local outputs [own_lo, own_hi)
+  if (i_hi <= i_lo) own_lo = own_hi = 0;
 
   HbStage<MA, G / 2, 0> sa;
   HbStage<MB, G / 4, 1> sb;
@@ -315,37 +482,38 @@ __global__ void __launch_bounds__(128) cascade_kernel(CascadeParams p) {
   HbStage<MD, G / 16, 3> sd;
   sa.reset(); sb.reset(); sc.reset(); sd.reset();
 
-  float vr = 0.0f, vi = 0.0f;
-  long long q = T0 - p.halo;
-  if (DC) {
-    if (q > 0) {
-      float2 v0 = p.v_seg[gid];
-      vr = v0.x; vi = v0.y;
-    }
-  }
-  if (q < 0) q = 0;
-
-  // arbitrary resampler state
+  // arbitrary resampler state (A.5): output j goes with input floor(j step / 2^24)
   float wr[13 + NO], wi[13 + NO];
-  unsigned phase = 0;
-  long long j = 0;
+  unsigned phase = 0, j32 = 0;
   if (ARB) {
 #pragma unroll
     for (int i = 0; i < 13 + NO; i++) wr[i] = wi[i] = 0.0f;
     if (i_lo > 0) {
-      unsigned long long num = (unsigned long long)i_lo << 24;
-      j = (long long)((num + p.step - 1) / p.step);
-      phase = (unsigned)((unsigned long long)j * p.step - num);
+      const unsigned long long num = (unsigned long long)i_lo << 24;
+      const unsigned long long j = (num + p.step - 1) / p.step;
+      phase = (unsigned)(j * p.step - num);
+      j32 = (unsigned)j;
     }
   }
   float2* dst = p.dst + (long long)s * p.dst_stride;
-  const long long q_end = i_hi * D;
+  const unsigned dmask = (unsigned)p.dst_mask;
+  const unsigned ob32 = (unsigned)ob;
   const float scale = p.scale;
 
-  for (; q < q_end; q += G) {
+  Loader<SRC> ld;
+  ld.template init<G>(p.src, s, qb);
+  Raw<SRC, G> cur;
+  ld.template fetch<G>(0, cur);
+  for (int it = 0; it < n_it; it++) {
+    Raw<SRC, G> nxt;
+    if (it + 1 < n_it) ld.template fetch<G>(it + 1, nxt);   // one group ahead
     float xr[G], xi[G];
-    Loader<SRC>::template load<G>(p.src, s, q, xr, xi);
-    if (DC) {
+    ld.template convert<G>(p.src, qb + (long long)it * G, it, cur, xr, xi);
+    cur = nxt;
+    if (DC == DC_ZSR) {
+      if (it == cap_it) p.sums[gid] = make_float2(vr, vi);
+    }
+    if (DC != DC_NONE) {
 #pragma unroll
       for (int i = 0; i < G; i++) {
         float yr = fmaf(-p.alpha, vr, xr[i]), yi = fmaf(-p.alpha, vi, xi[i]);
@@ -364,42 +532,48 @@ __global__ void __launch_bounds__(128) cascade_kernel(CascadeParams p) {
     if constexpr (MC > 0) { sc.run(p, br, bi, cr, ci, NST == 3 ? scale : 1.0f); outr = cr; outi = ci; }
     if constexpr (MD > 0) { sd.run(p, cr, ci, dr, di, NST == 4 ? scale : 1.0f); outr = dr; outi = di; }
 
-    const long long i0 = q / D;  // index of the first output of this iteration
+    const int o0 = it * NO;                       // local index of this iteration's first output
+    const int lo = own_lo - o0, hi = own_hi - o0; // owned b are [lo, hi)
+    const bool all = lo <= 0 && hi >= NO;
     if constexpr (!ARB) {
-      if (i0 >= i_lo && i0 + NO <= i_hi && (NO % 2 == 0)) {
-        float4* d4 = (float4*)(dst + (i0 & p.dst_mask));
+      if (all && (NO % 2 == 0)) {
+        float4* d4 = (float4*)(dst + ((ob32 + (unsigned)o0) & dmask));
 #pragma unroll
         for (int b = 0; b < NO / 2; b++) d4[b] = make_float4(outr[2 * b], outi[2 * b], outr[2 * b + 1], outi[2 * b + 1]);
-      } else {
+      } else if (hi > 0 && lo < NO) {
 #pragma unroll
         for (int b = 0; b < NO; b++)
-          if (i0 + b >= i_lo && i0 + b < i_hi) dst[(i0 + b) & p.dst_mask] = make_float2(outr[b], outi[b]);
+          if (b >= lo && b < hi) dst[(ob32 + (unsigned)(o0 + b)) & dmask] = make_float2(outr[b], outi[b]);
       }
     } else {
 #pragma unroll
       for (int b = 0; b < NO; b++) { wr[13 + b] = outr[b]; wi[13 + b] = outi[b]; }
+      if (hi > 0 && lo < NO) {
 #pragma unroll
-      for (int b = 0; b < NO; b++) {
-        if (i0 + b >= i_lo && i0 + b < i_hi) {
-          // A.5: emit outputs while phase < 2^24; newest sample is w[13 + b]
-#pragma unroll 1
-          while (phase < (1u << 24)) {
-            const float4* row = (const float4*)(p.pfb + ((phase >> (24 - p.bits)) << 4));
-            float4 h0 = __ldg(row), h1 = __ldg(row + 1), h2 = __ldg(row + 2), h3 = __ldg(row + 3);
-            float h[14] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w, h2.x, h2.y, h2.z, h2.w, h3.x, h3.y};
-            float yr = 0.0f, yi = 0.0f;
+        for (int b = 0; b < NO; b++) {
+          if (all || (b >= lo && b < hi)) {
+            // decimating plans have step >= 2^24: at most one output per pushed sample
+            if (phase < (1u << 24)) {
+              const float4* row = (const float4*)(p.pfb + ((phase >> (24 - p.bits)) << 4));
+              const float4 h0 = __ldg(row), h1 = __ldg(row + 1), h2 = __ldg(row + 2), h3 = __ldg(row + 3);
+              const float h[14] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w, h2.x, h2.y, h2.z, h2.w, h3.x, h3.y};
+              float yr = 0.0f, yi = 0.0f;
 #pragma unroll
-            for (int k = 0; k < 14; k++) { yr = fmaf(h[k], wr[13 + b - k], yr); yi = fmaf(h[k], wi[13 + b - k], yi); }
-            dst[j & p.dst_mask] = make_float2(yr, yi);
-            j++;
-            phase += p.step;
+              for (int k = 0; k < 14; k++) { yr = fmaf(h[k], wr[13 + b - k], yr); yi = fmaf(h[k], wi[13 + b - k], yi); }
+              dst[j32 & dmask] = make_float2(yr, yi);
+              j32++;
+              phase += p.step;
+            }
+            phase -= (1u << 24);
           }
-          phase -= (1u << 24);
         }
       }
 #pragma unroll
       for (int i = 0; i < 13; i++) { wr[i] = wr[NO + i]; wi[i] = wi[NO + i]; }
     }
+  }
+  if (DC == DC_ZSR) {
+    if (cap_it >= n_it) p.sums[gid] = make_float2(vr, vi);
   }
 }
 

@@ -1,0 +1,403 @@
+// Host-side owner of the front end: plans the multi-stage resampler as a short chain of
+// cascade_kernel launches, keeps the rings / raw history / DC-blocker carry, and turns one
+// execute() call into launches using closed-form absolute sample counts.  Device counterpart of
+// iirfilt_crcf + msresamp_crcf (/root/reference/src/sdr_pmr446.c:422-428,795-796;
+// src/dsd_in.c:97-101,167-168).
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common_host.hpp"
+#include "design.hpp"
+#include "frontend.cuh"
+
+namespace pmr {
+
+typedef void (*cascade_fn)(CascadeParams);
+
+// One cascade launch: a run of half-band stages (execution order, highest rate first), optionally
+// preceded by the DC blocker and followed by the arbitrary resampler.
+struct Level {
+  int src = SRC_RING;
+  int dc = DC_NONE;
+  bool arb = false;
+  int ms[4] = {0, 0, 0, 0};
+  int nst = 0, D = 1, G = 16, unit = 16, halo = 0, seg_len = 1024;
+  float hb[4][20];
+  float scale = 1.0f;
+  cascade_fn fn = nullptr;
+  DevBuf ring;            // output ring [S][cap] float2
+  long long cap = 0;
+  long long n_in = 0, n_out = 0;   // absolute counts: inputs seen, outputs written
+  long long max_in = 0, max_out = 0;  // per chunk
+};
+
+template <int SRC, int DC, int G, int A, int B, int C, int D, bool ARB>
+static cascade_fn cfn() { return cascade_kernel<SRC, DC, G, A, B, C, D, ARB>; }
+
+// Instantiated stage combinations; anything else is reported as unsupported.
+inline cascade_fn pick_cascade(int src, int dc, bool arb, const int* ms, int* G) {
+  auto is = [&](int a, int b, int c, int d) { return ms[0] == a && ms[1] == b && ms[2] == c && ms[3] == d; };
+  *G = 16;
+  if (!arb) {
+    if (dc == DC_ZSR && src == SRC_CU8) {
+      if (is(5, 0, 0, 0)) return cfn<SRC_CU8, DC_ZSR, 16, 5, 0, 0, 0, false>();
+      if (is(3, 5, 0, 0)) return cfn<SRC_CU8, DC_ZSR, 16, 3, 5, 0, 0, false>();
+      if (is(3, 3, 3, 3)) return cfn<SRC_CU8, DC_ZSR, 16, 3, 3, 3, 3, false>();
+    }
+    if (dc == DC_ZSR && src == SRC_CF32) {
+      if (is(5, 0, 0, 0)) return cfn<SRC_CF32, DC_ZSR, 16, 5, 0, 0, 0, false>();
+      if (is(3, 5, 0, 0)) return cfn<SRC_CF32, DC_ZSR, 16, 3, 5, 0, 0, false>();
+      if (is(3, 3, 3, 3)) return cfn<SRC_CF32, DC_ZSR, 16, 3, 3, 3, 3, false>();
+    }
+    if (dc == DC_NONE && src == SRC_CF32) {   // stand-alone msresamp_crcf (liquid shim): input is already DC-blocked
+      if (is(5, 0, 0, 0)) return cfn<SRC_CF32, DC_NONE, 16, 5, 0, 0, 0, false>();
+      if (is(3, 5, 0, 0)) return cfn<SRC_CF32, DC_NONE, 16, 3, 5, 0, 0, false>();
+      if (is(3, 3, 3, 3)) return cfn<SRC_CF32, DC_NONE, 16, 3, 3, 3, 3, false>();
+    }
+    if (dc == DC_NONE && src == SRC_RING) {
+      if (is(5, 0, 0, 0)) return cfn<SRC_RING, DC_NONE, 16, 5, 0, 0, 0, false>();
+      if (is(3, 5, 0, 0)) return cfn<SRC_RING, DC_NONE, 16, 3, 5, 0, 0, false>();
+    }
+  } else {
+    if (dc == DC_NONE && src == SRC_RING && is(10, 0, 0, 0)) { *G = 8; return cfn<SRC_RING, DC_NONE, 8, 10, 0, 0, 0, true>(); }
+    if (dc == DC_SCAN && src == SRC_CU8 && is(0, 0, 0, 0)) return cfn<SRC_CU8, DC_SCAN, 16, 0, 0, 0, 0, true>();
+    if (dc == DC_SCAN && src == SRC_CF32 && is(0, 0, 0, 0)) return cfn<SRC_CF32, DC_SCAN, 16, 0, 0, 0, 0, true>();
+    if (dc == DC_NONE && src == SRC_CF32 && is(0, 0, 0, 0)) return cfn<SRC_CF32, DC_NONE, 16, 0, 0, 0, 0, true>();
+  }
+  return nullptr;
+}
+
+struct Frontend {
+  int S = 0, fmt = 0;
+  bool dc = true;
+  float alpha = 0.0f, alpha_eff = 0.0f, c_pole = 1.0f;
+  design::MsresampPlan plan;
+  std::vector<Level> levels;
+  // level-0 raw history (two buffers, swapped every call)
+  DevBuf hist[2];
+  int hist_cur = 0;
+  long long hist_base = 0;
+  int hist_cap = 0;       // samples
+  int bps = 8;            // bytes per input sample
+  // DC blocker carry (A.1): V at (segment 0 start - halo) of the next chunk
+  DevBuf v_lag, sums, v_seg, e_table;
+  int max_seg0 = 0;
+  DevBuf pfb;
+  long long n_in = 0;     // raw samples consumed so far
+  struct OutView { void* p; } out;   // final ring (levels.back())
+  long long out_cap = 0, n_out = 0;
+  unsigned max_chunk = 0;
+
+  long long max_out_per_chunk() const { return levels.empty() ? 0 : levels.back().max_out; }
+
+  // E[k]: response of level 0's stage chain (zero state) to the sequence c^i, i >= 0, in float64
+  std::vector<float> zir_table(const Level& L) const {
+    const int n_in = L.halo + L.seg_len;
+    std::vector<double> x(n_in);
+    double v = 1.0;
+    for (int i = 0; i < n_in; i++) { x[i] = v; v *= (double)c_pole; }
+    for (int k = 0; k < L.nst; k++) {
+      const int m = L.ms[k];
+      std::vector<double> y(x.size() / 2);
+      for (size_t o = 0; o < y.size(); o++) {
+        const long long d = 2 * (long long)o + 1 - 2 * m;
+        double acc = d >= 0 ? x[d] : 0.0;
+        for (int j = 0; j < 2 * m; j++) {
+          const long long e = 2 * (long long)o - 2 * j;
+          if (e >= 0) acc += (double)L.hb[k][j] * x[e];
+        }
+        y[o] = acc;
+      }
+      x.swap(y);
+    }
+    std::vector<float> e(x.size());
+    for (size_t i = 0; i < x.size(); i++) e[i] = (float)(x[i] * (double)L.scale);
+    return e;
+  }
+
+  int init(int n_streams, int in_fmt, float rate, float as, bool with_dc, float dc_alpha, unsigned max_chunk_, long long extra_hist) {
+    S = n_streams;
+    fmt = in_fmt;
+    dc = with_dc;
+    alpha = dc_alpha;
+    // liquid stores a1 = -1 + alpha rounded to float32 and computes y = v[n] - v[n-1] with
+    // v[n] = x - a1 v[n-1]; the effective feedback is therefore 1 - fl(1 - alpha), not alpha.
+    c_pole = 1.0f - alpha;
+    alpha_eff = 1.0f - c_pole;
+    max_chunk = max_chunk_;
+    bps = (in_fmt == PMR446_FMT_CU8) ? 2 : 8;
+    if (rate > 1.0f) return fail(PMR446_EINVAL, "front end only decimates (rate <= 1)");
+    plan = design::msresamp_plan(rate, as);
+    if (plan.sub_len != 14) return fail(PMR446_EINVAL, "arbitrary resampler kernel is specialised for 14 taps");
+    if (plan.step < (1u << 24)) return fail(PMR446_EINVAL, "internal: decimating plan with arbitrary rate > 1");
+    // execution-order stage list: plan.m[stages-1] runs first
+    std::vector<int> order;
+    for (int g = (int)plan.stages - 1; g >= 0; g--) order.push_back((int)plan.m[g]);
+    std::vector<std::vector<int>> groups;   // pre-launch groups, then the arb launch
+    std::vector<int> last;
+    if (!order.empty()) { last.push_back(order.back()); order.pop_back(); }
+    for (size_t i = 0; i < order.size(); i += 4) groups.emplace_back(order.begin() + i, order.begin() + std::min(order.size(), i + 4));
+    groups.push_back(last);   // may be empty (rate >= 0.5)
+    levels.resize(groups.size());
+    long long max_in = max_chunk;
+    int stage_cursor = (int)plan.stages - 1;  // index into plan.m / plan.hb of the next stage to place
+    for (size_t l = 0; l < groups.size(); l++) {
+      Level& L = levels[l];
+      L.src = (l == 0) ? (in_fmt == PMR446_FMT_CU8 ? SRC_CU8 : SRC_CF32) : SRC_RING;
+      L.dc = (l == 0 && dc) ? (groups.size() >= 2 ? DC_ZSR : DC_SCAN) : DC_NONE;
+      L.arb = (l + 1 == groups.size());
+      L.nst = (int)groups[l].size();
+      L.D = 1 << L.nst;
+      memset(L.hb, 0, sizeof L.hb);
+      int halo = 0;
+      for (int k = 0; k < L.nst; k++) {
+        L.ms[k] = groups[l][k];
+        const std::vector<float>& t = plan.hb[stage_cursor];
+        for (size_t j = 0; j < t.size(); j++) L.hb[k][j] = t[j];
+        halo += (4 * L.ms[k] - 2 + 1) << k;
+        stage_cursor--;
+      }
+      if (L.arb) halo += 14 * L.D;
+      L.scale = 1.0f / (float)L.D;
+      L.fn = pick_cascade(L.src, L.dc, L.arb, L.ms, &L.G);
+      if (!L.fn) {
+        char msg[160];
+        snprintf(msg, sizeof msg, "resampler plan not built: level %zu src=%d dc=%d arb=%d stages=[%d,%d,%d,%d]", l, L.src, L.dc,
+                 (int)L.arb, L.ms[0], L.ms[1], L.ms[2], L.ms[3]);
+        return fail(PMR446_EINVAL, msg);
+      }
+      // segment granularity; a DC_ZSR producer aligns its grid to 16 ring samples so that the
+      // consumer's groups never straddle two producer segments (Loader<SRC_RING> correction)
+      L.unit = std::max(16, L.D);
+      if (L.dc == DC_ZSR) L.unit = std::max(L.unit, 16 * L.D);
+      L.halo = (halo + L.D + L.unit - 1) / L.unit * L.unit;
+      // segment length: as long as possible while keeping >= ~150k threads in flight
+      int seg = 4096;
+      int seg_min = 256;
+      while (seg_min < 4 * L.halo || seg_min < L.unit) seg_min <<= 1;
+      while (seg > seg_min && (long long)S * ((max_in + seg - 1) / seg) < 148LL * 1024) seg >>= 1;
+      L.seg_len = std::max(seg, seg_min);
+      if (L.arb) {
+        // equal resampler phase at every segment start (all lanes of a warp then emit outputs in
+        // lock-step) needs (seg_len / D) * 2^24 = 0 mod step
+        unsigned long long g = plan.step, b = 1ull << 24;
+        while (b) { unsigned long long tt = g % b; g = b; b = tt; }
+        const unsigned long long k = plan.step / g;
+        if (k > 1 && k <= 64) {
+          const long long q = (long long)k * std::max(L.unit, L.D);
+          L.seg_len = (int)std::max<long long>(q, L.seg_len / q * q);
+        }
+      }
+      L.max_in = max_in;
+      long long max_hb = max_in / L.D + 1;
+      L.max_out = L.arb ? (long long)design::arb_outputs_after((uint64_t)max_hb, plan.step) + 2 : max_hb;
+      long long need = L.max_out + 64 + (l + 1 < groups.size() ? 0 : extra_hist);
+      if (l + 1 < groups.size()) need += 4096;  // next level's halo (checked below)
+      L.cap = next_pow2(need);
+      if (int rc = L.ring.alloc_zero((size_t)S * L.cap * sizeof(float2))) return rc;
+      max_in = L.max_out;
+    }
+    for (size_t l = 1; l < levels.size(); l++)
+      if (levels[l].halo + 64 > 4096) return fail(PMR446_EINVAL, "internal: halo exceeds ring slack");
+    // arbitrary resampler bank, rows padded to 16 floats
+    std::vector<float> rows((size_t)plan.npfb * 16, 0.0f);
+    for (unsigned i = 0; i < plan.npfb; i++)
+      for (unsigned k = 0; k < plan.sub_len; k++) rows[(size_t)i * 16 + k] = plan.pfb[(size_t)i * plan.sub_len + k];
+    if (int rc = pfb.alloc(rows.size() * sizeof(float))) return rc;
+    CUDA_TRY(cudaMemcpy(pfb.p, rows.data(), rows.size() * sizeof(float), cudaMemcpyHostToDevice));
+    // raw history and DC carry
+    Level& L0 = levels[0];
+    hist_cap = L0.halo + L0.unit;
+    for (int i = 0; i < 2; i++)
+      if (int rc = hist[i].alloc_zero((size_t)S * hist_cap * bps)) return rc;
+    max_seg0 = (int)((max_chunk + 2 * L0.unit + L0.seg_len - 1) / L0.seg_len) + 2;
+    if (int rc = v_lag.alloc_zero((size_t)S * sizeof(float2))) return rc;
+    if (int rc = sums.alloc_zero((size_t)S * max_seg0 * sizeof(float2))) return rc;
+    if (int rc = v_seg.alloc_zero((size_t)S * max_seg0 * sizeof(float2))) return rc;
+    if (L0.dc == DC_ZSR) {
+      std::vector<float> e = zir_table(L0);
+      if (int rc = e_table.alloc((e.size() + 16) * sizeof(float))) return rc;
+      CUDA_TRY(cudaMemset(e_table.p, 0, e_table.bytes));
+      CUDA_TRY(cudaMemcpy(e_table.p, e.data(), e.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    reset_counters();
+    out.p = levels.back().ring.p;
+    out_cap = levels.back().cap;
+    return 0;
+  }
+
+  void reset_counters() {
+    n_in = 0;
+    n_out = 0;
+    hist_cur = 0;
+    hist_base = -(long long)levels[0].halo;
+    for (auto& L : levels) L.n_in = L.n_out = 0;
+  }
+  void reset() {
+    reset_counters();
+    for (auto& L : levels) cudaMemset(L.ring.p, 0, L.ring.bytes);
+    for (int i = 0; i < 2; i++) cudaMemset(hist[i].p, 0, hist[i].bytes);
+    cudaMemset(v_lag.p, 0, v_lag.bytes);
+  }
+
+  // Consumes n raw samples per stream ([n_in, n_in + n)); afterwards n_out is the absolute
+  // number of output samples in the `out` ring.
+  int execute(const void* iq, long long iq_stride, unsigned n, cudaStream_t st, int* launches, Timer* tm = nullptr) {
+    const long long n0 = n_in, n1 = n_in + n;
+    Timer dummy;
+    if (!tm) tm = &dummy;
+    SrcView v0;
+    memset(&v0, 0, sizeof v0);
+    v0.hist = hist[hist_cur].p;
+    v0.hist_stride = (long long)hist_cap * bps;
+    v0.hist_base = hist_base;
+    v0.cur = iq;
+    v0.cur_stride = iq_stride;
+    v0.n0 = n0;
+    v0.n1 = n1;
+    v0.cur_aligned = (n0 % 16 == 0) && (((uintptr_t)iq) % 16 == 0) && (iq_stride % 16 == 0);
+
+    Correction corr;               // set by a DC_ZSR level for its consumer
+    memset(&corr, 0, sizeof corr);
+    long long lvl_n0 = n0, lvl_n1 = n1;
+    for (size_t l = 0; l < levels.size(); l++) {
+      Level& L = levels[l];
+      const long long seg0 = lvl_n0 / L.unit * L.unit, seg0_next = lvl_n1 / L.unit * L.unit;
+      const long long out0 = lvl_n0 / L.D, out1 = lvl_n1 / L.D;
+      long long span = (out1 > out0) ? out1 * L.D - seg0 : seg0_next - seg0;
+      const int nseg = (int)((span + L.seg_len - 1) / L.seg_len);
+      SrcView sv;
+      if (l == 0) {
+        sv = v0;
+      } else {
+        const Level& P = levels[l - 1];
+        memset(&sv, 0, sizeof sv);
+        sv.cur = P.ring.p;
+        sv.cur_stride = P.cap * (long long)sizeof(float2);
+        sv.n0 = lvl_n0;
+        sv.n1 = lvl_n1;
+        sv.ring_mask = P.cap - 1;
+        sv.cur_aligned = 1;
+        sv.corr = corr;
+      }
+      const long long threads = (long long)S * nseg;
+      const unsigned blocks = (unsigned)((threads + 127) / 128);
+      DcScanParams sp;
+      if (L.dc != DC_NONE) {
+        if (nseg > max_seg0) return fail(PMR446_ERANGE, "internal: segment count exceeds allocation");
+        sp.n_streams = S;
+        sp.nseg = nseg;
+        sp.sums = (const float2*)sums.p;
+        sp.v_seg = (float2*)v_seg.p;
+        sp.v_lag = (float2*)v_lag.p;
+        sp.p0 = seg0 - L.halo;
+        sp.seg_len = L.seg_len;
+        sp.end = seg0_next - L.halo;
+        sp.c = c_pole;
+        sp.decay_full = (float)pow((double)c_pole, (double)L.seg_len);
+      }
+      if (L.dc == DC_SCAN && nseg > 0) {   // V0 per segment up front: local sums, then the scan
+        DcLocalParams dp;
+        dp.src = sv;
+        dp.n_streams = S;
+        dp.nseg = nseg;
+        dp.p0 = sp.p0;
+        dp.seg_len = L.seg_len;
+        dp.end = sp.end;
+        dp.c = c_pole;
+        dp.sums = (float2*)sums.p;
+        if (L.src == SRC_CU8) dc_local_kernel<SRC_CU8><<<blocks, 128, 0, st>>>(dp);
+        else dc_local_kernel<SRC_CF32><<<blocks, 128, 0, st>>>(dp);
+        dc_scan_kernel<<<(unsigned)(((long long)S * 32 + 127) / 128), 128, 0, st>>>(sp);
+        *launches += 2;
+        tm->mark(st, TM_DC);
+      }
+      long long new_out = L.n_out;
+      if (out1 > out0 || (L.dc == DC_ZSR && nseg > 0)) {
+        CascadeParams cp;
+        memset(&cp, 0, sizeof cp);
+        cp.src = sv;
+        cp.n_streams = S;
+        cp.nseg = nseg;
+        cp.seg0 = seg0;
+        cp.seg_len = L.seg_len;
+        cp.halo = L.halo;
+        cp.out0 = out0;
+        cp.out1 = out1;
+        cp.scale = L.scale;
+        cp.alpha = alpha_eff;
+        cp.v_seg = (const float2*)v_seg.p;
+        cp.sums = (float2*)sums.p;
+        cp.dc_end = seg0_next - L.halo;
+        cp.step = plan.step;
+        cp.bits = (int)plan.bits;
+        cp.pfb = (const float*)pfb.p;
+        cp.dst = (float2*)L.ring.p;
+        cp.dst_stride = L.cap;
+        cp.dst_mask = L.cap - 1;
+        memcpy(cp.hb, L.hb, sizeof cp.hb);
+        L.fn<<<blocks, 128, 0, st>>>(cp);
+        *launches += 1;
+        tm->mark(st, TM_CASCADE0 + (int)std::min<size_t>(l, 2));
+        if (out1 > out0) new_out = L.arb ? (long long)design::arb_outputs_after((uint64_t)out1, plan.step) : out1;
+      }
+      if (L.dc == DC_ZSR && nseg > 0) {   // chain the local sums the cascade just wrote into V0 per segment
+        dc_scan_kernel<<<(unsigned)(((long long)S * 32 + 127) / 128), 128, 0, st>>>(sp);
+        *launches += 1;
+        tm->mark(st, TM_DC);
+        int shift = 0;
+        while ((1 << shift) < L.seg_len / L.D) shift++;
+        corr.v_seg = (const float2*)v_seg.p;
+        corr.e = (const float*)e_table.p;
+        corr.from = out0;
+        corr.seg0_out = seg0 / L.D;
+        corr.seg_shift = shift;
+        corr.halo_out = L.halo / L.D;
+        corr.nseg = nseg;
+        corr.alpha = alpha_eff;
+        for (int i = 0; i < 16; i++) corr.rho_pow[i] = (float)pow((double)c_pole, (double)(i * L.D));
+      } else {
+        memset(&corr, 0, sizeof corr);
+      }
+      if (l > 0 && sv.corr.v_seg) {
+        // the consumer has read its input: fix the tail of the producer's ring in place, it is the
+        // next chunk's history
+        const Level& P = levels[l - 1];
+        const int count = L.halo + L.unit;
+        const long long start = lvl_n1 - count;
+        zir_tail_kernel<<<dim3((count + 127) / 128, S), 128, 0, st>>>((float2*)P.ring.p, P.cap, P.cap - 1, sv.corr, start, count);
+        *launches += 1;
+        tm->mark(st, TM_HIST);
+      }
+      L.n_in = lvl_n1;
+      lvl_n0 = L.n_out;
+      L.n_out = new_out;
+      lvl_n1 = new_out;
+    }
+    // save the raw tail for the next call
+    {
+      const Level& L0 = levels[0];
+      const long long new_base = n1 / L0.unit * L0.unit - L0.halo;
+      const int count = (int)(n1 - new_base);
+      if (count > hist_cap) return fail(PMR446_ERANGE, "internal: history overflow");
+      DevBuf& dst = hist[hist_cur ^ 1];
+      dim3 grid((count + 127) / 128, S);
+      if (count > 0) {
+        if (bps == 2) hist_update_kernel<uint16_t><<<grid, 128, 0, st>>>(v0, (uint16_t*)dst.p, hist_cap, new_base, count);
+        else hist_update_kernel<float2><<<grid, 128, 0, st>>>(v0, (float2*)dst.p, hist_cap, new_base, count);
+        *launches += 1;
+        tm->mark(st, TM_HIST);
+      }
+      hist_cur ^= 1;
+      hist_base = new_base;
+    }
+    n_in = n1;
+    n_out = levels.back().n_out;
+    return 0;
+  }
+};
+
+}  // namespace pmr

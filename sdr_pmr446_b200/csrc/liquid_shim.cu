@@ -16,6 +16,7 @@
 
 #include "../../include/pmr446_liquid_shim.h"
 #include "common_host.hpp"
+#include "frontend_host.hpp"
 #include "design.hpp"
 #include "dsd.cuh"
 #include "spectrum.cuh"

@@ -17,6 +17,7 @@
 #include "../../include/pmr446_taps.h"
 #include "backend.cuh"
 #include "common_host.hpp"
+#include "frontend_host.hpp"
 #include "design.hpp"
 #include "frontend.cuh"
 #include "spectrum.cuh"

@@ -32,6 +32,7 @@ if "pcm" in a.want:
 if "audio" in a.want:
     outs["audio"] = torch.empty((S, 16, ld), dtype=torch.float32, device="cuda")
 print("fp32 peak TFLOP/s", chain.measure_fp32_peak())
+b.timing(True)
 for it in range(a.steps + 2):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -41,3 +42,5 @@ for it in range(a.steps + 2):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     print("step %d: %.3f ms  %.1f Msps  ny=%d ns=%d launches=%d" % (it, ms, S * n / ms / 1e3, ny, ns, b.last_launches))
+tm = b.get_timings()
+print("per-kernel avg ms:", {k: round(v[0] / v[1], 3) for k, v in tm.items()})
