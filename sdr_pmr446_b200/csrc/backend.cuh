@@ -16,162 +16,6 @@
 namespace pmr {
 
 // ------------------------------------------------------------------------------------------
-// Channelizer.  One half-warp (16 lanes) walks a tile of frames of one stream; lane i is
-// polyphase branch i: it keeps its 26-sample window in registers (28 slots so the rotation has
-// period 28 = 7 float4 store groups), takes one mixed sample per frame (the commutator sends
-// sample 16f + 15 - i to branch i), does the 26-tap dot product and joins a 4-stage
-// decimation-in-frequency FFT over the 16 lanes with xor-shuffles.  After the FFT the lane with
-// DFT input index n = 15 - i holds bin bitrev4(n), i.e. PMR channel c = bitrev4(15 - i); it runs
-// the discriminator for that channel on consecutive frames and writes 4 frames per float4.
-struct ChanParams {
-  const float2* res;       // resampler output ring [n_streams][res_stride]
-  long long res_stride, res_mask;
-  long long r1;            // resampler outputs available: [.., r1)
-  int n_streams;
-  int tiles;               // tiles per stream
-  long long tile0;         // index of the first tile (tile k covers frames [k*TL, (k+1)*TL))
-  long long f0, f1;        // owned frames [f0, f1)
-  unsigned dtheta;         // NCO phase increment per sample (A.7)
-  float ref;               // 1 / (2 pi kf)
-  const float* taps;       // [16][26] branch taps, newest first
-  float* demod;            // ring [n_streams*16][demod_stride]
-  long long demod_stride, demod_mask;
-  float2* chan;            // optional: [n_streams][16][chan_ld], column = f - f0
-  long long chan_ld;
-};
-
-constexpr int CH_TL = 136;      // owned frames per tile (28*5 - 4)
-constexpr int CH_BLOCKS28 = 5;
-
-__device__ __forceinline__ float fast_atan2f(float y, float x) { return atan2f(y, x); }
-
-template <bool NCO_LUT>
-__global__ void __launch_bounds__(128) channelize16_kernel(ChanParams p) {
-  __shared__ float2 lut[32];
-  if (NCO_LUT) {
-    if (threadIdx.x < 32) {
-      float sn, cs;
-      sincospif((float)threadIdx.x * (1.0f / 16.0f), &sn, &cs);
-      lut[threadIdx.x] = make_float2(cs, sn);
-    }
-    __syncthreads();
-  }
-  const int lane16 = threadIdx.x & 15;
-  long long grp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
-  const bool active = grp < (long long)p.n_streams * p.tiles;
-  if (!active) grp = 0;  // keep the lanes alive for the shuffles; stores are masked below
-  const int s = (int)(grp / p.tiles);
-  const long long tile = p.tile0 + (grp % p.tiles);
-  const long long fa = tile * CH_TL;
-  const float2* res = p.res + (long long)s * p.res_stride;
-
-  float h[26];
-#pragma unroll
-  for (int n = 0; n < 26; n++) h[n] = __ldg(p.taps + lane16 * 26 + n);
-
-  // FFT constants of this lane: DFT input index n = 15 - lane16
-  const int nidx = 15 - lane16;
-  float sg[4], twr[3], twi[3];
-#pragma unroll
-  for (int st = 0; st < 4; st++) {
-    const int hh = 8 >> st;
-    const bool hi = (nidx & hh) != 0;
-    sg[st] = hi ? -1.0f : 1.0f;
-    if (st < 3) {
-      float sn = 0.0f, cs = 1.0f;
-      if (hi) sincospif(-(float)(nidx & (hh - 1)) / (float)hh, &sn, &cs);
-      twr[st] = cs;
-      twi[st] = sn;
-    }
-  }
-  const int c = ((nidx & 1) << 3) | ((nidx & 2) << 1) | ((nidx & 4) >> 1) | ((nidx & 8) >> 3);
-  float* drow = p.demod + ((long long)s * 16 + c) * p.demod_stride;
-  float2* crow = p.chan ? p.chan + ((long long)s * 16 + c) * p.chan_ld : nullptr;
-
-  auto fetch = [&](long long f, float& xr, float& xi) {
-    const long long j = 16 * f + 15 - lane16;
-    float2 v = make_float2(0.0f, 0.0f);
-    if (j >= 0 && j < p.r1) v = res[j & p.res_mask];
-    float cs, sn;
-    const unsigned th = (unsigned)j * p.dtheta;
-    if (NCO_LUT) {
-      float2 e = lut[th >> 27];
-      cs = e.x; sn = e.y;
-    } else {
-      sincospif((float)(int)th * (1.0f / 2147483648.0f), &sn, &cs);
-    }
-    xr = fmaf(v.x, cs, v.y * sn);    // v * conj(e^{j theta})
-    xi = fmaf(v.y, cs, -v.x * sn);
-  };
-
-  float wr[28], wi[28];
-  const long long fs = fa - 4;
-  wr[0] = wi[0] = wr[1] = wi[1] = wr[2] = wi[2] = 0.0f;
-#pragma unroll
-  for (int n = 1; n <= 25; n++) fetch(fs - n, wr[28 - n], wi[28 - n]);
-
-  float pr = 0.0f, pi = 0.0f;  // previous channel sample (discriminator state r_prime)
-  float dm[4];
-  float2 ch[4];
-#pragma unroll 1
-  for (int blk = 0; blk < CH_BLOCKS28; blk++) {
-    const long long fb = fs + 28 * blk;
-#pragma unroll
-    for (int ff = 0; ff < 28; ff++) {
-      const long long f = fb + ff;
-      fetch(f, wr[ff], wi[ff]);
-      float ar = 0.0f, ai = 0.0f;
-#pragma unroll
-      for (int n = 0; n < 26; n++) {
-        ar = fmaf(h[n], wr[(ff - n + 28) % 28], ar);
-        ai = fmaf(h[n], wi[(ff - n + 28) % 28], ai);
-      }
-      // 16-point DIF FFT across the half-warp
-#pragma unroll
-      for (int st = 0; st < 4; st++) {
-        const int hh = 8 >> st;
-        float br = __shfl_xor_sync(0xffffffffu, ar, hh);
-        float bi = __shfl_xor_sync(0xffffffffu, ai, hh);
-        float tr = fmaf(sg[st], ar, br), ti = fmaf(sg[st], ai, bi);
-        if (st < 3) {
-          ar = fmaf(tr, twr[st], -ti * twi[st]);
-          ai = fmaf(tr, twi[st], ti * twr[st]);
-        } else {
-          ar = tr; ai = ti;
-        }
-      }
-      // discriminator (A.9): arg(conj(prev) * y) * ref
-      // (separate mul/add like the C reference, so signed zeros at stream start behave the same)
-      if (f == 0) { pr = 0.0f; pi = 0.0f; }
-      const float re = __fadd_rn(__fmul_rn(pr, ar), __fmul_rn(pi, ai));
-      const float im = __fsub_rn(__fmul_rn(pr, ai), __fmul_rn(pi, ar));
-      dm[ff & 3] = fast_atan2f(im, re) * p.ref;
-      ch[ff & 3] = make_float2(ar, ai);
-      pr = ar; pi = ai;
-      if ((ff & 3) == 3 && active) {
-        const long long g0 = f - 3;
-        if (g0 >= p.f0 && f < p.f1 && g0 >= fa && f < fa + CH_TL) {
-          *(float4*)(drow + (g0 & p.demod_mask)) = make_float4(dm[0], dm[1], dm[2], dm[3]);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const long long fk = g0 + k;
-            if (fk >= p.f0 && fk < p.f1 && fk >= fa && fk < fa + CH_TL) drow[fk & p.demod_mask] = dm[k];
-          }
-        }
-        if (crow) {
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const long long fk = g0 + k;
-            if (fk >= p.f0 && fk < p.f1 && fk >= fa && fk < fa + CH_TL) crow[fk - p.f0] = ch[k];
-          }
-        }
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // Audio chain.  One block = one (stream, channel) row x one time tile.  Thread t owns 16
 // consecutive output samples; the tile's input (with a halo of taps-1 samples) sits in shared
 // memory with one pad word every 16 so that the per-thread sliding windows (lane stride 17

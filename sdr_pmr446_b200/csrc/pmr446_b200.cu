@@ -16,6 +16,7 @@
 #include "../../include/pmr446_b200.h"
 #include "../../include/pmr446_taps.h"
 #include "backend.cuh"
+#include "channelizer.cuh"
 #include "common_host.hpp"
 #include "frontend_host.hpp"
 #include "design.hpp"
@@ -237,8 +238,8 @@ extern "C" int pmr446_batch_execute_device(pmr446_batch* b, const void* iq, long
     cp.demod_mask = b->demod_cap - 1;
     cp.chan = (float2*)out->chan;
     cp.chan_ld = out->ld;
-    long long groups = (long long)S * cp.tiles;
-    unsigned blocks = (unsigned)((groups * 16 + 127) / 128);
+    long long warps = (long long)S * cp.tiles;   // one warp per (stream, frame tile)
+    unsigned blocks = (unsigned)((warps * 32 + 127) / 128);
     if (b->nco_lut) channelize16_kernel<true><<<blocks, 128, 0, st>>>(cp);
     else channelize16_kernel<false><<<blocks, 128, 0, st>>>(cp);
     b->launches++;
