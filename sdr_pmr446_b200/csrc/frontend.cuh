@@ -89,11 +89,26 @@ struct CascadeParams {
 template <int SRC, int G>
 struct Raw;
 template <int G>
-struct Raw<SRC_CU8, G> { uint4 v[G / 8]; };
+struct Raw<SRC_CU8, G> { unsigned w[G / 2]; };   // 2 bytes per sample
 template <int G>
-struct Raw<SRC_CF32, G> { float4 v[G / 2]; };
+struct Raw<SRC_CF32, G> { unsigned w[2 * G]; };  // 8 bytes per sample
 template <int G>
-struct Raw<SRC_RING, G> { float4 v[G / 2]; };
+struct Raw<SRC_RING, G> { unsigned w[2 * G]; };
+
+// 256-bit global accesses (LDG/STG.E.ENL2.256 on sm_100): a lane's 32-byte piece is one DRAM sector and,
+// with every lane on a different cache line, costs one L1 wavefront instead of two 128-bit ones.
+__device__ __forceinline__ void ldg256_stream(const void* p, unsigned* w) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
+}
+__device__ __forceinline__ void ldg256(const void* p, unsigned* w) {
+  asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void stg256(void* p, const float* f) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(p), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]), "f"(f[4]), "f"(f[5]),
+               "f"(f[6]), "f"(f[7]) : "memory");
+}
 
 // Per-thread loader state: `fast` means every group of the thread's range can be read with aligned
 // vector loads from one place, so fetch() is a pointer bump; otherwise each sample is guarded.
@@ -107,7 +122,7 @@ template <>
 struct Loader<SRC_CU8> {
   const uint8_t* hist;
   const uint8_t* cur;
-  const uint4* fp;
+  const uint8_t* fp;
   int fast_lo, fast_hi;   // iterations [fast_lo, fast_hi) read whole aligned groups of the current chunk
   template <int G>
   __device__ __forceinline__ void init(const SrcView& v, int s, long long qb) {
@@ -119,13 +134,14 @@ struct Loader<SRC_CU8> {
       fast_lo = (int)(lo < 0 ? 0 : (lo > (1 << 30) ? (1 << 30) : lo));
       fast_hi = (int)(hi < 0 ? 0 : (hi > (1 << 30) ? (1 << 30) : hi));
     }
-    fp = (const uint4*)(cur + 2 * (qb - v.n0));
+    fp = cur + 2 * (qb - v.n0);
   }
   template <int G>
   __device__ __forceinline__ void fetch(int it, Raw<SRC_CU8, G>& r) const {
+    static_assert(G % 16 == 0, "cu8 groups are loaded 32 bytes at a time");
     if (it >= fast_lo && it < fast_hi) {
 #pragma unroll
-      for (int i = 0; i < G / 8; i++) r.v[i] = __ldg(fp + it * (G / 8) + i);
+      for (int i = 0; i < G / 16; i++) ldg256_stream(fp + (size_t)it * (2 * G) + 32 * i, r.w + 8 * i);
     }
   }
   // converts with the SoapyRTLSDR rule (u8 - 127.4)/128
@@ -134,15 +150,11 @@ struct Loader<SRC_CU8> {
     const float k = 1.0f / 128.0f, c0 = -127.4f / 128.0f;
     if (it >= fast_lo && it < fast_hi) {
 #pragma unroll
-      for (int i = 0; i < G / 8; i++) {
-        const unsigned ww[4] = {r.v[i].x, r.v[i].y, r.v[i].z, r.v[i].w};
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          xr[i * 8 + 2 * j] = fmaf(u8f(ww[j], 0), k, c0);
-          xi[i * 8 + 2 * j] = fmaf(u8f(ww[j], 1), k, c0);
-          xr[i * 8 + 2 * j + 1] = fmaf(u8f(ww[j], 2), k, c0);
-          xi[i * 8 + 2 * j + 1] = fmaf(u8f(ww[j], 3), k, c0);
-        }
+      for (int j = 0; j < G / 2; j++) {   // one 32-bit word = two samples
+        xr[2 * j] = fmaf(u8f(r.w[j], 0), k, c0);
+        xi[2 * j] = fmaf(u8f(r.w[j], 1), k, c0);
+        xr[2 * j + 1] = fmaf(u8f(r.w[j], 2), k, c0);
+        xi[2 * j + 1] = fmaf(u8f(r.w[j], 3), k, c0);
       }
     } else {
 #pragma unroll
@@ -166,7 +178,7 @@ template <>
 struct Loader<SRC_CF32> {
   const float2* hist;
   const float2* cur;
-  const float4* fp;
+  const float2* fp;
   int fast_lo, fast_hi;
   template <int G>
   __device__ __forceinline__ void init(const SrcView& v, int s, long long qb) {
@@ -178,22 +190,20 @@ struct Loader<SRC_CF32> {
       fast_lo = (int)(lo < 0 ? 0 : (lo > (1 << 30) ? (1 << 30) : lo));
       fast_hi = (int)(hi < 0 ? 0 : (hi > (1 << 30) ? (1 << 30) : hi));
     }
-    fp = (const float4*)(cur + (qb - v.n0));
+    fp = cur + (qb - v.n0);
   }
   template <int G>
   __device__ __forceinline__ void fetch(int it, Raw<SRC_CF32, G>& r) const {
     if (it >= fast_lo && it < fast_hi) {
 #pragma unroll
-      for (int i = 0; i < G / 2; i++) r.v[i] = __ldg(fp + it * (G / 2) + i);
+      for (int i = 0; i < G / 4; i++) ldg256_stream(fp + (size_t)it * G + 4 * i, r.w + 8 * i);
     }
   }
   template <int G>
   __device__ __forceinline__ void convert(const SrcView& v, long long q, int it, const Raw<SRC_CF32, G>& r, float* xr, float* xi) const {
     if (it >= fast_lo && it < fast_hi) {
 #pragma unroll
-      for (int i = 0; i < G / 2; i++) {
-        xr[2 * i] = r.v[i].x; xi[2 * i] = r.v[i].y; xr[2 * i + 1] = r.v[i].z; xi[2 * i + 1] = r.v[i].w;
-      }
+      for (int i = 0; i < G; i++) { xr[i] = __uint_as_float(r.w[2 * i]); xi[i] = __uint_as_float(r.w[2 * i + 1]); }
     } else {
 #pragma unroll
       for (int i = 0; i < G; i++) {
@@ -234,18 +244,16 @@ struct Loader<SRC_RING> {
   template <int G>
   __device__ __forceinline__ void fetch(int it, Raw<SRC_RING, G>& r) const {
     if (it < fast_hi) {
-      const float4* p = (const float4*)(ring + ((q32 + (unsigned)(it * G)) & mask32));
+      const float2* p = ring + ((q32 + (unsigned)(it * G)) & mask32);
 #pragma unroll
-      for (int i = 0; i < G / 2; i++) r.v[i] = p[i];
+      for (int i = 0; i < G / 4; i++) ldg256(p + 4 * i, r.w + 8 * i);
     }
   }
   template <int G>
   __device__ __forceinline__ void convert(const SrcView& v, long long q, int it, const Raw<SRC_RING, G>& r, float* xr, float* xi) const {
     if (it < fast_hi) {
 #pragma unroll
-      for (int i = 0; i < G / 2; i++) {
-        xr[2 * i] = r.v[i].x; xi[2 * i] = r.v[i].y; xr[2 * i + 1] = r.v[i].z; xi[2 * i + 1] = r.v[i].w;
-      }
+      for (int i = 0; i < G; i++) { xr[i] = __uint_as_float(r.w[2 * i]); xi[i] = __uint_as_float(r.w[2 * i + 1]); }
     } else {
 #pragma unroll
       for (int i = 0; i < G; i++) {
@@ -441,7 +449,7 @@ static __global__ void zir_tail_kernel(float2* ring, long long ring_stride, long
 // Stage list MA,MB,MC,MD = semi-lengths in execution order (highest rate first), 0 = absent.
 // G = input samples per loop iteration (multiple of 2^NST).
 template <int SRC, int DC, int G, int MA, int MB, int MC, int MD, bool ARB>
-__global__ void __launch_bounds__(128) cascade_kernel(CascadeParams p) {
+__global__ void __launch_bounds__(128, 3) cascade_kernel(CascadeParams p) {
   constexpr int NST = (MA > 0) + (MB > 0) + (MC > 0) + (MD > 0);
   constexpr int D = 1 << NST;
   constexpr int NO = G / D;  // outputs per iteration
@@ -484,8 +492,11 @@ __global__ void __launch_bounds__(128) cascade_kernel(CascadeParams p) {
 
   // arbitrary resampler state (A.5): output j goes with input floor(j step / 2^24)
   float wr[13 + NO], wi[13 + NO];
+  float obr[4], obi[4];            // four outputs (one 32-byte sector) are gathered per store
   unsigned phase = 0, j32 = 0;
   if (ARB) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) obr[i] = obi[i] = 0.0f;
 #pragma unroll
     for (int i = 0; i < 13 + NO; i++) wr[i] = wi[i] = 0.0f;
     if (i_lo > 0) {
@@ -495,6 +506,7 @@ __global__ void __launch_bounds__(128) cascade_kernel(CascadeParams p) {
       j32 = (unsigned)j;
     }
   }
+  unsigned ob_first = j32 & 3u;   // first slot of the current group of four that belongs to this segment
   float2* dst = p.dst + (long long)s * p.dst_stride;
   const unsigned dmask = (unsigned)p.dst_mask;
   const unsigned ob32 = (unsigned)ob;
@@ -536,7 +548,14 @@ __global__ void __launch_bounds__(128) cascade_kernel(CascadeParams p) {
     const int lo = own_lo - o0, hi = own_hi - o0; // owned b are [lo, hi)
     const bool all = lo <= 0 && hi >= NO;
     if constexpr (!ARB) {
-      if (all && (NO % 2 == 0)) {
+      if (all && (NO % 4 == 0)) {
+        float2* d2 = dst + ((ob32 + (unsigned)o0) & dmask);
+#pragma unroll
+        for (int b = 0; b < NO / 4; b++) {
+          const float f[8] = {outr[4 * b], outi[4 * b], outr[4 * b + 1], outi[4 * b + 1], outr[4 * b + 2], outi[4 * b + 2], outr[4 * b + 3], outi[4 * b + 3]};
+          stg256(d2 + 4 * b, f);
+        }
+      } else if (all && (NO % 2 == 0)) {
         float4* d4 = (float4*)(dst + ((ob32 + (unsigned)o0) & dmask));
 #pragma unroll
         for (int b = 0; b < NO / 2; b++) d4[b] = make_float4(outr[2 * b], outi[2 * b], outr[2 * b + 1], outi[2 * b + 1]);
@@ -560,7 +579,22 @@ __global__ void __launch_bounds__(128) cascade_kernel(CascadeParams p) {
               float yr = 0.0f, yi = 0.0f;
 #pragma unroll
               for (int k = 0; k < 14; k++) { yr = fmaf(h[k], wr[13 + b - k], yr); yi = fmaf(h[k], wi[13 + b - k], yi); }
-              dst[j32 & dmask] = make_float2(yr, yi);
+              const unsigned slot = j32 & 3u;
+#pragma unroll
+              for (int sl = 0; sl < 4; sl++)
+                if (slot == (unsigned)sl) { obr[sl] = yr; obi[sl] = yi; }
+              if (slot == 3u) {
+                float2* d2 = dst + ((j32 - 3u) & dmask);
+                if (ob_first == 0u) {
+                  const float f[8] = {obr[0], obi[0], obr[1], obi[1], obr[2], obi[2], obr[3], obi[3]};
+                  stg256(d2, f);
+                } else {
+#pragma unroll
+                  for (int sl = 1; sl < 4; sl++)
+                    if ((unsigned)sl >= ob_first) d2[sl] = make_float2(obr[sl], obi[sl]);
+                  ob_first = 0u;
+                }
+              }
               j32++;
               phase += p.step;
             }
@@ -571,6 +605,13 @@ __global__ void __launch_bounds__(128) cascade_kernel(CascadeParams p) {
 #pragma unroll
       for (int i = 0; i < 13; i++) { wr[i] = wr[NO + i]; wi[i] = wi[NO + i]; }
     }
+  }
+  if (ARB) {   // outputs of an unfinished group of four
+    const unsigned pend = j32 & 3u;
+    float2* d2 = dst + ((j32 - pend) & dmask);
+#pragma unroll
+    for (int sl = 0; sl < 3; sl++)
+      if ((unsigned)sl >= ob_first && (unsigned)sl < pend) d2[sl] = make_float2(obr[sl], obi[sl]);
   }
   if (DC == DC_ZSR) {
     if (cap_it >= n_it) p.sums[gid] = make_float2(vr, vi);

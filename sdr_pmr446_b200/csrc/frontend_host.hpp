@@ -258,7 +258,8 @@ struct Frontend {
     v0.cur_stride = iq_stride;
     v0.n0 = n0;
     v0.n1 = n1;
-    v0.cur_aligned = (n0 % 16 == 0) && (((uintptr_t)iq) % 16 == 0) && (iq_stride % 16 == 0);
+    // fast path: 256-bit vector loads straight from the caller's buffer
+    v0.cur_aligned = (n0 % 16 == 0) && (((uintptr_t)iq) % 32 == 0) && (iq_stride % 32 == 0);
 
     Correction corr;               // set by a DC_ZSR level for its consumer
     memset(&corr, 0, sizeof corr);
