@@ -1,33 +1,27 @@
-// Back-end kernels of the PMR446 chain.
-//
-//  channelize16_kernel : NCO mix-down + 16-channel polyphase analysis filter bank + 16-point DFT
-//                        + NBFM discriminator.  Replaces the inner loop
-//                        /root/reference/src/sdr_pmr446.c:804-823 (nco_crcf_mix_down/step,
-//                        firpfbch_crcf_analyzer_execute, transpose) and freqdem_demodulate_block
-//                        (:881) for every channel.
-//  audio_kernel        : 377-tap CTCSS-removal high-pass FIR, complementary low-pass branch,
-//                        audio gain, 1-pole de-emphasis, optional 103-tap low-pass, s16 conversion.
-//                        Replaces :882-902 (firfilt_rrrf_execute_block, wdelayf, iirfilt_rrrf)
-//                        (Appendix A.1, A.10, A.11) and the s16 cast of src/dsd_in.c:172-175.
+// audio_kernel: 377-tap CTCSS-removal high-pass FIR, complementary low-pass branch, audio gain,
+// 1-pole de-emphasis, optional 103-tap low-pass, s16 conversion.  Replaces
+// /root/reference/src/sdr_pmr446.c:882-902 (firfilt_rrrf_execute_block, wdelayf, iirfilt_rrrf;
+// SURVEY.md Appendix A.1, A.10, A.11) for every channel, and the s16 cast of src/dsd_in.c:172-175.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace pmr {
 
-// ------------------------------------------------------------------------------------------
-// Audio chain.  One block = one (stream, channel) row x one time tile.  Thread t owns 16
-// consecutive output samples; the tile's input (with a halo of taps-1 samples) sits in shared
-// memory with one pad word every 16 so that the per-thread sliding windows (lane stride 17
-// words) are bank-conflict free.  The FIR runs 16 taps x 16 outputs per step from registers:
-// 256 FFMA per 16 LDS (samples) + 4 LDS.128 (broadcast taps).
+// One block = one (stream, channel) row x one time tile.  Thread t owns 16 consecutive output
+// samples; the tile's input (with a halo of taps-1 samples) sits in shared memory with one pad
+// word every 16 so that the per-thread sliding windows (lane stride 17 words) are bank-conflict
+// free.  The FIR runs 16 taps x 16 outputs per step from registers: 256 FFMA per 16 LDS (samples)
+// + 4 LDS.128 (broadcast taps).  The first `lead` outputs of a tile are lead-in (de-emphasis
+// warm-up, low-pass halo) and are not stored; threads whose outputs are not needed skip the FIR.
 struct AudioParams {
   const float* demod;      // ring [rows][demod_stride]
   long long demod_stride, demod_mask;
   int rows;                // n_streams * 16
   int tiles;               // tiles per row
-  long long tile0;         // tile k covers outputs [k*TT, (k+1)*TT), TT = AU_OWN
+  long long tile0;         // tile k covers outputs [k*own, (k+1)*own), own = AU_SPAN - lead
   long long f0, f1;        // owned samples
+  int lead;                // lead-in outputs per tile (multiple of 16; 16 without, 128 with the low-pass)
   const float* hp_taps;    // [HP_PAD] zero-padded to a multiple of 16
   int hp_chunks;           // HP_PAD / 16
   int hp_delay;            // (hp_len - 1) / 2
@@ -43,8 +37,8 @@ struct AudioParams {
 
 constexpr int AU_THREADS = 128;
 constexpr int AU_SPAN = AU_THREADS * 16;   // outputs computed per tile (incl. lead-in)
-constexpr int AU_LEAD = 128;               // lead-in outputs (de-emphasis warm-up + LP halo), multiple of 16
-constexpr int AU_OWN = AU_SPAN - AU_LEAD;  // owned outputs per tile
+constexpr int AU_LEAD_LP = 128;            // lead-in with the 103-tap low-pass (>= 112 + 8)
+constexpr int AU_LEAD_MIN = 16;            // lead-in without it (de-emphasis warm-up of 8)
 constexpr int AU_MAXHALO = 384;            // >= padded HP length
 
 __device__ __forceinline__ int padidx(int i) { return i + (i >> 4); }
@@ -93,48 +87,72 @@ __global__ void __launch_bounds__(AU_THREADS) audio_kernel(AudioParams p) {
   constexpr int XN = AU_MAXHALO + AU_SPAN + 16;
   float* xs = smem;
   float* ys = smem + padidx(XN) + 1;
-  float* ts = ys + padidx(AU_LEAD + AU_SPAN + 16) + 1;   // taps (16-byte aligned below)
+  float* ts = ys + padidx(AU_LEAD_LP + AU_SPAN + 16) + 1;   // taps (16-byte aligned below)
   ts = (float*)(((uintptr_t)ts + 15) & ~(uintptr_t)15);
 
   const int row = blockIdx.x / p.tiles;
+  const int lead = p.lead, own = AU_SPAN - lead;
   const long long tile = p.tile0 + blockIdx.x % p.tiles;
-  const long long o0 = tile * AU_OWN - AU_LEAD;   // absolute index of computed output 0 (multiple of 16)
+  const long long o0 = tile * own - lead;   // absolute index of computed output 0 (multiple of 16)
   const float* drow = p.demod + (long long)row * p.demod_stride;
   const int t = threadIdx.x;
+  // everything below is 32-bit and relative to o0
+  const long long lo64 = p.f0 - o0, hi64 = p.f1 - o0;
+  const int f0r = (int)(lo64 < -(1 << 28) ? -(1 << 28) : lo64);                 // first owned output, relative
+  const int f1r = (int)(hi64 > (1 << 28) ? (1 << 28) : hi64);                   // one past the last available input/output
+  const int z0r = (int)(-o0 > (1 << 28) ? (1 << 28) : (-o0 < -(1 << 28) ? -(1 << 28) : -o0));   // stream start, relative
 
-  // load x[o0 - AU_MAXHALO .. o0 + AU_SPAN) ; negative absolute indices are zero (stream start)
-  for (int i = t; i < AU_MAXHALO + AU_SPAN; i += AU_THREADS) {
-    const long long n = o0 - AU_MAXHALO + i;
-    xs[padidx(i)] = (n >= 0 && n < p.f1) ? drow[n & p.demod_mask] : 0.0f;
+  // load x[o0 - AU_MAXHALO .. o0 + AU_SPAN): four samples per thread and step; negative absolute
+  // indices (before the stream start) and samples not yet produced read as zero
+  {
+    const unsigned base32 = (unsigned)(o0 - AU_MAXHALO), dmask = (unsigned)p.demod_mask;
+    for (int i = 4 * t; i < AU_MAXHALO + AU_SPAN; i += 4 * AU_THREADS) {
+      const int rel = i - AU_MAXHALO;   // relative to o0
+      float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (rel >= z0r && rel + 4 <= f1r) {
+        v = *(const float4*)(drow + ((base32 + (unsigned)i) & dmask));
+      } else if (rel + 4 > z0r && rel < f1r) {
+        const float* q = drow;
+        if (rel + 0 >= z0r && rel + 0 < f1r) v.x = q[(base32 + (unsigned)i + 0u) & dmask];
+        if (rel + 1 >= z0r && rel + 1 < f1r) v.y = q[(base32 + (unsigned)i + 1u) & dmask];
+        if (rel + 2 >= z0r && rel + 2 < f1r) v.z = q[(base32 + (unsigned)i + 2u) & dmask];
+        if (rel + 3 >= z0r && rel + 3 < f1r) v.w = q[(base32 + (unsigned)i + 3u) & dmask];
+      }
+      float* d = xs + padidx(i);
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
   }
   const int hp_n = p.hp_chunks * 16, lp_n = p.lp_taps ? p.lp_chunks * 16 : 0;
   for (int i = t; i < hp_n; i += AU_THREADS) ts[i] = p.hp_taps[i];
   for (int i = t; i < lp_n; i += AU_THREADS) ts[hp_n + i] = p.lp_taps[i];
   __syncthreads();
 
+  // is any of this thread's 16 outputs stored, or needed as lead-in by a stored one?
+  const int ob = 16 * t;                                     // relative index of this thread's first output
+  const bool need = (ob < f1r) && (ob + 16 + lead > f0r);
+
   // high-pass FIR: outputs o0 + 16 t + r
   float acc[16];
 #pragma unroll
   for (int r = 0; r < 16; r++) acc[r] = 0.0f;
   const int top = AU_MAXHALO + 16 * t;
-  fir16(xs, ts, top, p.hp_chunks, acc);
+  if (need) fir16(xs, ts, top, p.hp_chunks, acc);
 
-  const long long obase = o0 + 16 * t;
-  const bool own_thread = (16 * t >= AU_LEAD);
+  const bool own_thread = (ob >= lead);
   // complementary low-pass branch (A.11): delayed input minus high-pass output
-  if (p.lpcomp && own_thread) {
+  if (p.lpcomp && own_thread && need) {
     float* lrow = p.lpcomp + (long long)row * p.out_ld;
 #pragma unroll
     for (int r = 0; r < 16; r++) {
-      const long long f = obase + r;
-      if (f >= p.f0 && f < p.f1) lrow[f - p.f0] = xs[padidx(top + r - p.hp_delay)] - acc[r];
+      const int f = ob + r;
+      if (f >= f0r && f < f1r) lrow[f - f0r] = xs[padidx(top + r - p.hp_delay)] - acc[r];
     }
   }
   // gain, then de-emphasis (A.1, Direct Form II): v = x - a1 v1 ; y = b0 v + b1 v1
 #pragma unroll
   for (int r = 0; r < 16; r++) {
     acc[r] *= p.gain;
-    ys[padidx(AU_LEAD + 16 * t + r)] = acc[r];
+    ys[padidx(AU_LEAD_LP + 16 * t + r)] = acc[r];
   }
   __syncthreads();
   {
@@ -142,8 +160,8 @@ __global__ void __launch_bounds__(AU_THREADS) audio_kernel(AudioParams p) {
     float v1 = 0.0f;
 #pragma unroll
     for (int k = 8; k >= 1; k--) {
-      const int idx = AU_LEAD + 16 * t - k;
-      const float xv = (idx >= AU_LEAD) ? ys[padidx(idx)] : 0.0f;
+      const int idx = AU_LEAD_LP + 16 * t - k;
+      const float xv = (idx >= AU_LEAD_LP) ? ys[padidx(idx)] : 0.0f;
       v1 = fmaf(-p.de_a1, v1, xv);
     }
 #pragma unroll
@@ -156,15 +174,15 @@ __global__ void __launch_bounds__(AU_THREADS) audio_kernel(AudioParams p) {
   if (p.lp_taps) {
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < 16; r++) ys[padidx(AU_LEAD + 16 * t + r)] = acc[r];
-    if (t < AU_LEAD / 16) {
+    for (int r = 0; r < 16; r++) ys[padidx(AU_LEAD_LP + 16 * t + r)] = acc[r];
+    if (t < AU_LEAD_LP / 16) {
 #pragma unroll
       for (int r = 0; r < 16; r++) ys[padidx(16 * t + r)] = 0.0f;
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < 16; r++) acc[r] = 0.0f;
-    fir16(ys, ts + hp_n, AU_LEAD + 16 * t, p.lp_chunks, acc);
+    if (need && own_thread) fir16(ys, ts + hp_n, AU_LEAD_LP + 16 * t, p.lp_chunks, acc);
   }
   // stage through shared memory for coalesced, arbitrarily aligned stores
   __syncthreads();
@@ -173,14 +191,11 @@ __global__ void __launch_bounds__(AU_THREADS) audio_kernel(AudioParams p) {
   __syncthreads();
   float* arow = p.audio ? p.audio + (long long)row * p.out_ld : nullptr;
   short* prow = p.pcm ? p.pcm + (long long)row * p.out_ld : nullptr;
-  const long long own_lo = o0 + AU_LEAD, own_hi = o0 + AU_SPAN;
-  for (int i = AU_LEAD + t; i < AU_SPAN; i += AU_THREADS) {
-    const long long f = o0 + i;
-    if (f >= p.f0 && f < p.f1 && f >= own_lo && f < own_hi) {
-      const float v = xs[padidx(i)];
-      if (arow) arow[f - p.f0] = v;
-      if (prow) prow[f - p.f0] = (short)__float2int_rz(v * 32767.0f);
-    }
+  const int s_lo = lead > f0r ? lead : f0r, s_hi = AU_SPAN < f1r ? AU_SPAN : f1r;   // stored outputs, relative
+  for (int i = s_lo + t; i < s_hi; i += AU_THREADS) {
+    const float v = xs[padidx(i)];
+    if (arow) arow[i - f0r] = v;
+    if (prow) prow[i - f0r] = (short)__float2int_rz(v * 32767.0f);
   }
 }
 

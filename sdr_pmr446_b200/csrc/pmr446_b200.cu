@@ -118,7 +118,7 @@ extern "C" int pmr446_batch_create(const pmr446_config* cfg, pmr446_batch** out)
   b->nco_lut = (b->dtheta & ((1u << 27) - 1)) == 0;
 
   // demod ring: history for the audio FIR halo + one chunk
-  b->demod_cap = next_pow2(b->max_ns + AU_MAXHALO + AU_LEAD + 64);
+  b->demod_cap = next_pow2(b->max_ns + AU_MAXHALO + AU_LEAD_LP + 64);
   if ((rc = b->d_demod.alloc_zero((size_t)S * 16 * b->demod_cap * sizeof(float)))) { pmr446_batch_destroy(b); return rc; }
 
   // audio filters
@@ -130,7 +130,7 @@ extern "C" int pmr446_batch_create(const pmr446_config* cfg, pmr446_batch** out)
   const float* lpt = cfg->lp_taps ? cfg->lp_taps : lp.data();
   unsigned lpn = cfg->lp_taps ? cfg->lp_len : (unsigned)lp.size();
   if (hpn < 1 || hpn > (unsigned)AU_MAXHALO || (hpn & 1) == 0) { pmr446_batch_destroy(b); return fail(PMR446_EINVAL, "hp_len must be odd and <= 383"); }
-  if (lpn < 1 || lpn > (unsigned)AU_LEAD - 16) { pmr446_batch_destroy(b); return fail(PMR446_EINVAL, "lp_len must be <= 112"); }
+  if (lpn < 1 || lpn > (unsigned)AU_LEAD_LP - 16) { pmr446_batch_destroy(b); return fail(PMR446_EINVAL, "lp_len must be <= 112"); }
   b->hp_delay = (int)(hpn - 1) / 2;  // wdelayf_create((HP_AUDIO_FILT_TAPS - 1) / 2), :447
   if ((rc = upload_padded_taps(hpt, hpn, b->d_hp, &b->hp_chunks)) || (rc = upload_padded_taps(lpt, lpn, b->d_lp, &b->lp_chunks))) {
     pmr446_batch_destroy(b);
@@ -187,7 +187,7 @@ extern "C" int pmr446_batch_reset(pmr446_batch* b) {
 }
 
 static size_t audio_smem_bytes() {
-  size_t xn = AU_MAXHALO + AU_SPAN + 16, yn = AU_LEAD + AU_SPAN + 16;
+  size_t xn = AU_MAXHALO + AU_SPAN + 16, yn = AU_LEAD_LP + AU_SPAN + 16;
   return ((xn + xn / 16 + 1) + (yn + yn / 16 + 1) + 384 + 128 + 8) * sizeof(float);
 }
 
@@ -258,8 +258,10 @@ extern "C" int pmr446_batch_execute_device(pmr446_batch* b, const void* iq, long
       ap.demod_stride = b->demod_cap;
       ap.demod_mask = b->demod_cap - 1;
       ap.rows = S * 16;
-      ap.tile0 = f0 / AU_OWN;
-      ap.tiles = (int)((f1 + AU_OWN - 1) / AU_OWN - ap.tile0);
+      ap.lead = b->cfg.lowpass ? AU_LEAD_LP : AU_LEAD_MIN;
+      const long long own = AU_SPAN - ap.lead;
+      ap.tile0 = f0 / own;
+      ap.tiles = (int)((f1 + own - 1) / own - ap.tile0);
       ap.f0 = f0;
       ap.f1 = f1;
       ap.hp_taps = (const float*)b->d_hp.p;
