@@ -114,9 +114,11 @@ __global__ void __launch_bounds__(128) channelize16_kernel(ChanParams p) {
     const unsigned th = (jb32 + 16u * (unsigned)par) * p.dtheta;
     sincospif((float)(int)th * (1.0f / 2147483648.0f), &ps[par], &pc[par]);
   }
-  auto fetch = [&](int k) -> float2 {
-    float2 v = make_float2(0.0f, 0.0f);
-    if (k >= k_lo && k < k_hi) v = res[(jb32 + 16u * (unsigned)k) & rmask];
+  auto fetch = [&](int k) -> float2 {   // branch-free: out-of-range frames read slot 0 of the ring and are zeroed
+    const bool ok = k >= k_lo && k < k_hi;
+    const unsigned idx = ok ? ((jb32 + 16u * (unsigned)k) & rmask) : 0u;
+    float2 v = res[idx];
+    if (!ok) v = make_float2(0.0f, 0.0f);
     return v;
   };
   auto mix = [&](float2 v, int k, int par, float& xr, float& xi) {   // par = k & 1, passed as a literal
@@ -142,7 +144,9 @@ __global__ void __launch_bounds__(128) channelize16_kernel(ChanParams p) {
   const int own_lo = (int)(lo64 < 0 ? 0 : (lo64 > 4096 ? 4096 : lo64)), own_hi = (int)(hi64 < 0 ? 0 : (hi64 > 4096 ? 4096 : hi64));
   const unsigned fs32 = (unsigned)fs, dmask = (unsigned)p.demod_mask;
   const int crel = (int)(fs - p.f0 < -(1ll << 30) ? -(1 << 30) : (fs - p.f0 > (1ll << 30) ? (1 << 30) : fs - p.f0));
-  const bool first_is_stream_start = (fs + hsel <= 0);   // some computed frame may be frame 0
+  // computed frame k of this lane is absolute frame 0 (stream start: r_prime = 0) when k == k_zero
+  const long long kz64 = -fs - hsel;
+  const int k_zero = (int)(kz64 < -1 ? -1 : (kz64 > 4096 ? -1 : kz64));
 
   float sav_r = 0.0f, sav_i = 0.0f;   // half 0: y of the previous odd frame (from half 1)
   float2 n0 = fetch(0), n1 = fetch(1);
@@ -186,24 +190,21 @@ __global__ void __launch_bounds__(128) channelize16_kernel(ChanParams p) {
       const float exr = __shfl_xor_sync(0xffffffffu, ar, 16), exi = __shfl_xor_sync(0xffffffffu, ai, 16);
       float pr = hsel ? exr : sav_r, pi = hsel ? exi : sav_i;
       sav_r = exr; sav_i = exi;
-      if (first_is_stream_start && fs + k + hsel == 0) { pr = 0.0f; pi = 0.0f; }
+      if (k == k_zero) { pr = 0.0f; pi = 0.0f; }
       const float re = __fadd_rn(__fmul_rn(pr, ar), __fmul_rn(pi, ai));
       const float im = __fsub_rn(__fmul_rn(pr, ai), __fmul_rn(pi, ar));
       const float dm = fast_atan2f(im, re) * p.ref;
       const float dm_o = __shfl_xor_sync(0xffffffffu, dm, 16);
-      // half 0 stores frames k, k + 1 (own value and the other half's)
-      if (hsel == 0 && k + 1 >= own_lo && k < own_hi) {
+      // half 0 stores frames k, k + 1 (own value and the other half's); (fs + k) is even, so the pair
+      // is an aligned float2 unless the ownership boundary splits it
+      {
+        const bool a0 = (hsel == 0) && k >= own_lo && k < own_hi, a1 = (hsel == 0) && k + 1 >= own_lo && k + 1 < own_hi;
         float* d = drow + ((fs32 + (unsigned)k) & dmask);
-        if (k >= own_lo && k + 1 < own_hi) {
-          *(float2*)d = make_float2(dm, dm_o);
-        } else if (k >= own_lo) {
-          d[0] = dm;
-        } else {
-          drow[(fs32 + (unsigned)k + 1u) & dmask] = dm_o;
-        }
+        if (a0) d[0] = dm;
+        if (a1) d[1] = dm_o;
         if (crow) {
-          if (k >= own_lo) crow[crel + k] = make_float2(ar, ai);
-          if (k + 1 < own_hi) crow[crel + k + 1] = make_float2(exr, exi);
+          if (a0) crow[crel + k] = make_float2(ar, ai);
+          if (a1) crow[crel + k + 1] = make_float2(exr, exi);
         }
       }
     }

@@ -46,9 +46,10 @@ struct pmr446_batch {
   // waterfall
   Waterfall wf;
   // staging for the host-buffer call
-  DevBuf d_in, d_out_res, d_out_chan, d_out_demod, d_out_lpcomp, d_out_audio, d_out_pcm, d_out_ascii, d_out_peak, d_out_psd;
+  DevBuf d_in2[2], d_out_res, d_out_chan, d_out_demod, d_out_lpcomp, d_out_audio, d_out_pcm, d_out_ascii, d_out_peak, d_out_psd;
   long long max_res = 0, max_ns = 0;
-  cudaStream_t own_stream = nullptr;
+  cudaStream_t own_stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   int launches = 0;
   Timer timer;
 };
@@ -141,6 +142,11 @@ extern "C" int pmr446_batch_create(const pmr446_config* cfg, pmr446_batch** out)
   }
   cudaFuncSetAttribute(audio_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   CUDA_TRY(cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) {
+    CUDA_TRY(cudaEventCreateWithFlags(&b->ev_copied[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&b->ev_free[i], cudaEventDisableTiming));
+  }
   CUDA_TRY(cudaDeviceSynchronize());
   *out = b;
   return PMR446_OK;
@@ -151,6 +157,11 @@ extern "C" int pmr446_batch_destroy(pmr446_batch* b) {
   cudaSetDevice(b->device);
   cudaDeviceSynchronize();
   if (b->own_stream) cudaStreamDestroy(b->own_stream);
+  if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
+  for (int i = 0; i < 2; i++) {
+    if (b->ev_copied[i]) cudaEventDestroy(b->ev_copied[i]);
+    if (b->ev_free[i]) cudaEventDestroy(b->ev_free[i]);
+  }
   delete b;
   return PMR446_OK;
 }
@@ -299,18 +310,24 @@ extern "C" int pmr446_batch_execute(pmr446_batch* b, const void* iq, long long i
   if (!b || !out || (!iq && n)) return fail(PMR446_EINVAL, "null argument");
   if (n > b->cfg.max_chunk) return fail(PMR446_ERANGE, "chunk larger than max_chunk");
   cudaSetDevice(b->device);
-  cudaStream_t st = b->own_stream;
+  cudaStream_t st = b->own_stream, cs = b->copy_stream;
   const int S = b->S, M = 16;
   const size_t bps = b->cfg.in_fmt == PMR446_FMT_CU8 ? 2 : 8;
-  // device staging, sized once for the largest chunk
-  const long long in_row = (long long)((b->cfg.max_chunk * bps + 63) / 64 * 64);
-  int rc;
-  if ((rc = b->d_in.ensure((size_t)S * in_row))) return rc;
+  const unsigned W = b->cfg.waterfall;
   if (iq_stride < (long long)(n * bps)) {   // a single stream may pass stride 0
     if (S > 1) return fail(PMR446_EINVAL, "iq_stride smaller than one stream's chunk");
     iq_stride = (long long)(n * bps);
   }
-  if (n) CUDA_TRY(cudaMemcpy2DAsync(b->d_in.p, in_row, iq, iq_stride, (size_t)n * bps, S, cudaMemcpyHostToDevice, st));
+  // Large chunks are cut in time into sub-chunks so that the host->device copy of sub-chunk k+1 overlaps
+  // the kernels of sub-chunk k (all filter state carries across execute_device calls, so the result is the
+  // same).  Not done when a waterfall row is requested: asgram produces one row per call (:911-912).
+  const bool want_wf = W && (out->ascii || out->peak || out->psd);
+  const unsigned K = (!want_wf && n >= 8u * 65536u) ? 8u : 1u;
+  const unsigned sub = K == 1 ? n : ((n + K - 1) / K + 255u) / 256u * 256u;
+  const long long pitch = ((long long)(sub ? sub : 1) * (long long)bps + 255) / 256 * 256;
+  int rc;
+  for (int i = 0; i < (K > 1 ? 2 : 1); i++)
+    if ((rc = b->d_in2[i].ensure((size_t)S * pitch))) return rc;
   pmr446_outputs d = *out;
   const long long ld = b->max_ns, rld = b->max_res;
   d.ld = ld;
@@ -320,7 +337,6 @@ extern "C" int pmr446_batch_execute(pmr446_batch* b, const void* iq, long long i
     if (buf.ensure(bytes)) return nullptr;
     return buf.p;
   };
-  const unsigned W = b->cfg.waterfall;
   d.res = (float*)stage(out->res, b->d_out_res, (size_t)S * rld * 8);
   d.chan = (float*)stage(out->chan, b->d_out_chan, (size_t)S * M * ld * 8);
   d.demod = (float*)stage(out->demod, b->d_out_demod, (size_t)S * M * ld * 4);
@@ -330,9 +346,35 @@ extern "C" int pmr446_batch_execute(pmr446_batch* b, const void* iq, long long i
   d.ascii = (char*)stage(W ? out->ascii : nullptr, b->d_out_ascii, (size_t)S * W);
   d.peak = (float*)stage(W ? out->peak : nullptr, b->d_out_peak, (size_t)S * 2 * 4);
   d.psd = (float*)stage(W ? out->psd : nullptr, b->d_out_psd, (size_t)S * 4 * W * 4);
-  unsigned ny = 0, ns = 0;
-  rc = pmr446_batch_execute_device(b, b->d_in.p, in_row, n, &d, &ny, &ns, st);
-  if (rc) return rc;
+  unsigned ny_tot = 0, ns_tot = 0;
+  int launches = 0;
+  unsigned off = 0;
+  for (unsigned k = 0; k == 0 || off < n; k++) {
+    const unsigned len = std::min(sub, n - off);
+    const int buf = (int)(k & 1u);
+    if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(cs, b->ev_free[buf], 0));   // kernels of sub-chunk k-2 have read this buffer
+    if (len) CUDA_TRY(cudaMemcpy2DAsync(b->d_in2[buf].p, pitch, (const char*)iq + (size_t)off * bps, iq_stride, (size_t)len * bps, S,
+                                        cudaMemcpyHostToDevice, cs));
+    CUDA_TRY(cudaEventRecord(b->ev_copied[buf], cs));
+    CUDA_TRY(cudaStreamWaitEvent(st, b->ev_copied[buf], 0));
+    pmr446_outputs dk = d;
+    if (dk.res) dk.res += 2 * (size_t)ny_tot;
+    if (dk.chan) dk.chan += 2 * (size_t)ns_tot;
+    if (dk.demod) dk.demod += ns_tot;
+    if (dk.lpcomp) dk.lpcomp += ns_tot;
+    if (dk.audio) dk.audio += ns_tot;
+    if (dk.pcm) dk.pcm += ns_tot;
+    unsigned ny = 0, ns = 0;
+    rc = pmr446_batch_execute_device(b, b->d_in2[buf].p, pitch, len, &dk, &ny, &ns, st);
+    if (rc) return rc;
+    launches += b->launches;
+    CUDA_TRY(cudaEventRecord(b->ev_free[buf], st));
+    ny_tot += ny;
+    ns_tot += ns;
+    off += len;
+  }
+  b->launches = launches;
+  const unsigned ny = ny_tot, ns = ns_tot;
   if (out->res && ny > out->res_ld) return fail(PMR446_ERANGE, "res_ld too small");
   if ((out->chan || out->demod || out->lpcomp || out->audio || out->pcm) && ns > out->ld) return fail(PMR446_ERANGE, "ld too small");
   auto back = [&](void* host, const void* dev, long long hld, long long dld, size_t elt, long long rows, long long cols) {

@@ -140,3 +140,10 @@ def test_reset_restarts_the_stream():
     gpu.close()
     for k in ("res", "chan", "audio", "pcm"):
         assert np.array_equal(a[k], b[k]), k
+
+
+def test_large_chunk_time_sliced_host_call():
+    """Chunks >= 512 Ki samples are cut into 8 time slices inside pmr446_batch_execute (copy/compute overlap);
+    the result must not change."""
+    g, refs, car = _run_pair(2400000, 1200000, 600000, streams=2)
+    _check(g, refs, car)
