@@ -17,6 +17,7 @@
 #include "../../include/pmr446_taps.h"
 #include "backend.cuh"
 #include "channelizer.cuh"
+#include "channelizer_generic.cuh"
 #include "common_host.hpp"
 #include "frontend_host.hpp"
 #include "design.hpp"
@@ -34,7 +35,10 @@ struct pmr446_batch {
   int device = 0;
   Frontend fe;               // DC + msresamp -> resampled ring
   // channelizer
-  DevBuf d_pfb_taps;
+  int M = 16;                // channels
+  bool generic = false;      // generic-M kernel instead of the 16-channel register kernel
+  DevBuf d_pfb_taps, d_mixed, d_tw;
+  std::vector<int> radix;
   unsigned dtheta = 0;
   bool nco_lut = false;
   // demod ring [S*16][cap]
@@ -94,33 +98,58 @@ extern "C" int pmr446_batch_create(const pmr446_config* cfg, pmr446_batch** out)
   if (!cfg || !out) return fail(PMR446_EINVAL, "null argument");
   *out = nullptr;
   if (cfg->n_streams < 1 || cfg->max_chunk < 1 || cfg->fs_in == 0) return fail(PMR446_EINVAL, "bad n_streams/max_chunk/fs_in");
-  if (cfg->num_channels != 16) return fail(PMR446_EINVAL, "only the 16-channel PMR446 channelizer is built in this round");
-  if (cfg->pfb_m != 13) return fail(PMR446_EINVAL, "channelizer kernel is specialised for m = 13 (26 taps per branch)");
+  if (cfg->num_channels < 2 || cfg->num_channels > 4096 || cfg->pfb_m < 1 || cfg->pfb_m > 32)
+    return fail(PMR446_EINVAL, "num_channels must be in [2, 4096] and pfb_m in [1, 32]");
   if (int rc = select_device(cfg->device)) return rc;
   pmr446_batch* b = new pmr446_batch();
   b->cfg = *cfg;
   b->S = cfg->n_streams;
   cudaGetDevice(&b->device);
   const int S = b->S;
+  const int M = b->M = (int)cfg->num_channels;
+  b->generic = !(M == 16 && cfg->pfb_m == 13);   // the register-window kernel is specialised for 16 x 26 taps
 
   float fs_res = (float)(cfg->num_channels * cfg->channel_width);
   int rc = b->fe.init(S, cfg->in_fmt, fs_res / (float)cfg->fs_in, cfg->resamp_as, true, cfg->dc_alpha, cfg->max_chunk,
-                      /*extra_hist=*/(long long)std::max(16u * 32u, cfg->waterfall) + 64);
+                      /*extra_hist=*/std::max<long long>((long long)M * (2 * cfg->pfb_m + CG_FT + 4), (long long)cfg->waterfall) + 64);
   if (rc) { pmr446_batch_destroy(b); return rc; }
   b->max_res = b->fe.max_out_per_chunk();
-  b->max_ns = b->max_res / 16 + 1;
+  b->max_ns = b->max_res / M + 1;
 
   // channelizer (A.7, A.8)
-  std::vector<float> taps = design::pfbch_taps(16, cfg->pfb_m, cfg->pfb_as);
+  std::vector<float> taps = design::pfbch_taps((unsigned)M, cfg->pfb_m, cfg->pfb_as);
   if ((rc = b->d_pfb_taps.alloc(taps.size() * sizeof(float)))) { pmr446_batch_destroy(b); return rc; }
   cudaMemcpy(b->d_pfb_taps.p, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice);
   float offset = -0.5f * (float)(cfg->num_channels - 1) / (float)cfg->num_channels * 2 * M_PI;  // :432-433
   b->dtheta = design::nco_dtheta(offset);
   b->nco_lut = (b->dtheta & ((1u << 27) - 1)) == 0;
+  if (b->generic) {
+    unsigned nn = (unsigned)M;
+    while (nn % 4 == 0) { b->radix.push_back(4); nn /= 4; }
+    for (unsigned pr = 2; nn > 1;) {
+      if (nn % pr == 0) { b->radix.push_back((int)pr); nn /= pr; }
+      else pr++;
+    }
+    for (int r : b->radix)
+      if (r > 61 || b->radix.size() > 16) { pmr446_batch_destroy(b); return fail(PMR446_EINVAL, "num_channels has a prime factor > 61"); }
+    std::vector<float2> tw(M);
+    for (int k = 0; k < M; k++) {
+      double a = -2.0 * M_PI * (double)k / (double)M;
+      tw[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    if ((rc = b->d_tw.alloc((size_t)M * sizeof(float2))) || (rc = b->d_mixed.alloc_zero((size_t)S * b->fe.out_cap * sizeof(float2)))) {
+      pmr446_batch_destroy(b);
+      return rc;
+    }
+    cudaMemcpy(b->d_tw.p, tw.data(), (size_t)M * sizeof(float2), cudaMemcpyHostToDevice);
+    const size_t smem = (size_t)M * (3 * sizeof(float2) + CG_FT * sizeof(float));
+    if (smem > 200 * 1024) { pmr446_batch_destroy(b); return fail(PMR446_EINVAL, "num_channels too large for the shared-memory FFT"); }
+    cudaFuncSetAttribute(channelize_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
 
   // demod ring: history for the audio FIR halo + one chunk
   b->demod_cap = next_pow2(b->max_ns + AU_MAXHALO + AU_LEAD_LP + 64);
-  if ((rc = b->d_demod.alloc_zero((size_t)S * 16 * b->demod_cap * sizeof(float)))) { pmr446_batch_destroy(b); return rc; }
+  if ((rc = b->d_demod.alloc_zero((size_t)S * M * b->demod_cap * sizeof(float)))) { pmr446_batch_destroy(b); return rc; }
 
   // audio filters
   std::vector<float> hp(PMR446_HP_AUDIO_TAPS_LEN), lp(PMR446_LP_AUDIO_TAPS_LEN);
@@ -218,7 +247,8 @@ extern "C" int pmr446_batch_execute_device(pmr446_batch* b, const void* iq, long
   if (rc) return rc;
   r1 = b->fe.n_out;
   const long long ny = r1 - r0;
-  const long long f0 = r0 / 16, f1 = r1 / 16, ns = f1 - f0;  // frames: cbuffer carry of r % 16 samples (:804)
+  const int M = b->M;
+  const long long f0 = r0 / M, f1 = r1 / M, ns = f1 - f0;  // frames: cbuffer carry of r % M samples (:804)
   if (out->res && ny > out->res_ld) return fail(PMR446_ERANGE, "res_ld too small");
   if ((out->chan || out->demod || out->lpcomp || out->audio || out->pcm) && ns > out->ld) return fail(PMR446_ERANGE, "ld too small");
 
@@ -229,7 +259,38 @@ extern "C" int pmr446_batch_execute_device(pmr446_batch* b, const void* iq, long
     b->timer.mark(st, TM_GATHER);
   }
 
-  if (ns > 0) {
+  if (ns > 0 && b->generic) {
+    // ---- generic-M channelizer: mix once per sample, then FFT-based analysis bank ------------------
+    nco_mix_kernel<<<dim3((unsigned)((ny + 255) / 256), S), 256, 0, st>>>((const float2*)b->fe.out.p, (float2*)b->d_mixed.p, b->fe.out_cap,
+                                                                          b->fe.out_cap - 1, r0, ny, b->dtheta);
+    ChanGenParams gp;
+    memset(&gp, 0, sizeof gp);
+    gp.mixed = (const float2*)b->d_mixed.p;
+    gp.stride = b->fe.out_cap;
+    gp.mask = b->fe.out_cap - 1;
+    gp.r1 = r1;
+    gp.n_streams = S;
+    gp.M = M;
+    gp.p = 2 * (int)b->cfg.pfb_m;
+    gp.tile0 = f0 / CG_FT;
+    gp.tiles = (int)((f1 + CG_FT - 1) / CG_FT - gp.tile0);
+    gp.f0 = f0;
+    gp.f1 = f1;
+    gp.ref = 1.0f / (2 * M_PI * b->cfg.kf);
+    gp.taps = (const float*)b->d_pfb_taps.p;
+    gp.twiddle = (const float2*)b->d_tw.p;
+    gp.n_stages = (int)b->radix.size();
+    for (size_t i = 0; i < b->radix.size(); i++) gp.radix[i] = b->radix[i];
+    gp.demod = (float*)b->d_demod.p;
+    gp.demod_stride = b->demod_cap;
+    gp.demod_mask = b->demod_cap - 1;
+    gp.chan = (float2*)out->chan;
+    gp.chan_ld = out->ld;
+    const size_t smem = (size_t)M * (3 * sizeof(float2) + CG_FT * sizeof(float));
+    channelize_generic_kernel<<<(unsigned)((long long)S * gp.tiles), 256, smem, st>>>(gp);
+    b->launches += 2;
+    b->timer.mark(st, TM_CHANNELIZE);
+  } else if (ns > 0) {
     // ---- channelizer + discriminator --------------------------------------------------------
     ChanParams cp;
     cp.res = (const float2*)b->fe.out.p;
@@ -255,9 +316,10 @@ extern "C" int pmr446_batch_execute_device(pmr446_batch* b, const void* iq, long
     else channelize16_kernel<false><<<blocks, 128, 0, st>>>(cp);
     b->launches++;
     b->timer.mark(st, TM_CHANNELIZE);
-
+  }
+  if (ns > 0) {
     if (out->demod) {
-      gather_ring_kernel<float><<<dim3((unsigned)((ns + 255) / 256), S * 16), 256, 0, st>>>((const float*)b->d_demod.p, b->demod_cap,
+      gather_ring_kernel<float><<<dim3((unsigned)((ns + 255) / 256), S * M), 256, 0, st>>>((const float*)b->d_demod.p, b->demod_cap,
                                                                                            b->demod_cap - 1, f0, ns, out->demod, out->ld);
       b->launches++;
       b->timer.mark(st, TM_GATHER);
@@ -268,7 +330,7 @@ extern "C" int pmr446_batch_execute_device(pmr446_batch* b, const void* iq, long
       ap.demod = (const float*)b->d_demod.p;
       ap.demod_stride = b->demod_cap;
       ap.demod_mask = b->demod_cap - 1;
-      ap.rows = S * 16;
+      ap.rows = S * M;
       ap.lead = b->cfg.lowpass ? AU_LEAD_LP : AU_LEAD_MIN;
       const long long own = AU_SPAN - ap.lead;
       ap.tile0 = f0 / own;
@@ -311,7 +373,7 @@ extern "C" int pmr446_batch_execute(pmr446_batch* b, const void* iq, long long i
   if (n > b->cfg.max_chunk) return fail(PMR446_ERANGE, "chunk larger than max_chunk");
   cudaSetDevice(b->device);
   cudaStream_t st = b->own_stream, cs = b->copy_stream;
-  const int S = b->S, M = 16;
+  const int S = b->S, M = b->M;
   const size_t bps = b->cfg.in_fmt == PMR446_FMT_CU8 ? 2 : 8;
   const unsigned W = b->cfg.waterfall;
   if (iq_stride < (long long)(n * bps)) {   // a single stream may pass stride 0

@@ -147,3 +147,33 @@ def test_large_chunk_time_sliced_host_call():
     the result must not change."""
     g, refs, car = _run_pair(2400000, 1200000, 600000, streams=2)
     _check(g, refs, car)
+
+
+def test_wideband_1600_channels_cf32():
+    """BASELINE config 4 (shortened): 20 Msps cf32, 1600 channels of 12.5 kHz -- resampler rate 1.0 (no
+    half-band stage), generic-M channelizer.  GPU chunks are not frame aligned."""
+    from oracle import oracle as orc
+    from sdr_pmr446_b200 import chain, synth
+    M, fs, n = 1600, 20_000_000, 1_600_000
+    car = (synth.Carrier(3, 0.2, 1000.0, 67.0), synth.Carrier(800, 0.1, 600.0, 88.5),
+           synth.Carrier(801, 0.15, 1700.0, 123.0), synth.Carrier(1599, 0.05, 2400.0, 250.3))
+    spec = synth.CaptureSpec(fs=float(fs), num_channels=M, carriers=car)
+    iq = np.stack([synth.make_cf32(spec, n, 446), synth.make_cf32(spec, n, 447)])
+    want = ("res", "chan", "demod", "audio", "pcm")
+    gpu = chain.PmrBatch(n_streams=2, fs_in=fs, in_fmt=0, num_channels=M, max_chunk=400000)
+    g = gpu.run(iq, 333333, want)
+    gpu.close()
+    for s in range(2):
+        o = orc.PmrOracle(fs_in=fs, in_fmt=0, num_channels=M, chunk=400000)
+        r = o.run(iq[s], 400000)
+        o.close()
+        assert g["ny"] == r["ny"] and g["ns"] == r["ns"] == n // M
+        assert rel_rms(g["res"][s], r["res"]) < REL_RMS_TOL
+        assert rel_rms(g["chan"][s], r["chan"]) < REL_RMS_TOL
+        for c in active_channels(car):
+            assert rel_rms(g["chan"][s, c], r["chan"][c]) < REL_RMS_TOL, ("chan", s, c)
+            sl = slice(1, None) if g["demod"][s, c, 0] == r["demod"][c, 0] else slice(500, None)
+            assert rel_rms(g["demod"][s, c, sl], r["demod"][c, sl]) < REL_RMS_TOL, ("demod", s, c)
+            assert rel_rms(g["audio"][s, c, sl], r["audio"][c, sl]) < REL_RMS_TOL, ("audio", s, c)
+            dp = np.abs(g["pcm"][s, c, sl].astype(np.int32) - r["pcm"][c, sl].astype(np.int32))
+            assert dp.max() <= PCM_TOL_LSB, ("pcm", s, c, int(dp.max()))
