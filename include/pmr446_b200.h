@@ -110,6 +110,71 @@ int pmr446_batch_reset(pmr446_batch *b);
 int pmr446_batch_timing(pmr446_batch *b, int enable);
 int pmr446_batch_get_timings(pmr446_batch *b, double *total_ms, long long *count, int n);
 
+/* ---- receiver: RSSI, squelch / channel selector, selected-channel audio, CTCSS detector ---------
+ * What the reference actually plays: per chunk it measures every enabled channel
+ * (average_power, src/sdr_pmr446.c:330-336; find_max_rssi_channel, :668-700), runs the
+ * scanning/tuned state machine (:828-874) and demodulates ONLY the active channel through one
+ * freqdem / FIR / delay / de-emphasis chain whose state carries over channel changes (:876-908);
+ * the complementary low-pass branch feeds a DC blocker and a 38-tone Goertzel bank over blocks of
+ * 2441 samples (ctcss_execute :605-628, ctcss_detector_analyze :365-407).  One call = one chunk
+ * of every stream; the state machine runs on the GPU, one thread per stream, no host round trip. */
+#define PMR446_LOCK_START 0    /* lock_mode_start: stay on the first channel that opened the squelch */
+#define PMR446_LOCK_MAX 1      /* lock_mode_max: follow the strongest channel (:848-857) */
+#define PMR446_CTCSS_TONES 38  /* CTCSS_NUM_FREQS, include/sdr_pmr446.h:14 */
+#define PMR446_EV_TUNED 1      /* "Tuned to channel" :838 */
+#define PMR446_EV_CHANGED 2    /* "Changed active channel" :852 */
+#define PMR446_EV_DETUNED 4    /* "Detuned from channel" :861 */
+#define PMR446_EV_CTCSS_ACQUIRED 8   /* :616 */
+#define PMR446_EV_CTCSS_CHANGED 16   /* :619 */
+#define PMR446_EV_CTCSS_LOST 32      /* :624 */
+
+typedef struct {
+  pmr446_config chain;             /* DSP parameters; num_channels <= 64 (MAX_CHANNELS, :18) */
+  float squelch_level;             /* -s, SDR_DEFAULT_SQUELCH_LEVEL :34 (18 dB); closes 5 dB lower (:859) */
+  unsigned long long channel_mask; /* -m, bit i enables channel i (:155, :678) */
+  int lock_mode;                   /* PMR446_LOCK_* (:156) */
+  unsigned ctcss_block;            /* CTCSS_BLOCK_SIZE :46 (2441) */
+  float ctcss_dc_alpha;            /* :450 (0.0005) */
+} pmr446_rx_config;
+
+typedef struct {
+  int state;            /* proc_scanning 0 / proc_tuned 1 after this chunk (include/sdr_pmr446.h:17-21) */
+  int active_chan;      /* chain->active_chan: -1 or 0-based channel */
+  float rssi;           /* chain->rssi: strongest - mean of the enabled channels, dB */
+  unsigned n_audio;     /* audio samples this call appended for the stream (0 or ns) */
+  int tone_detected;    /* ctcss_detector->tone_detected */
+  int ctcss_index;      /* ctcss_detector->max_power_index (code - 1) */
+  float ctcss_freq;     /* chain->ctcss_freq: -1 at start, tone table entry, 0 after a detune */
+  float max_power;      /* ctcss_detector->max_power */
+  int events;           /* PMR446_EV_* raised by this chunk (the reference's LOG lines) */
+} pmr446_rx_status;
+
+/* Host pointers for pmr446_receiver_execute(), device pointers for _execute_device(); any may be NULL. */
+typedef struct {
+  float *rssi;               /* [n_streams][M] average_power per channel, dB */
+  pmr446_rx_status *status;  /* [n_streams] */
+  float *audio;              /* [n_streams][ld] selected-channel audio (what :903-905 queues for the DAC) */
+  int16_t *pcm;              /* [n_streams][ld] */
+  float *ctcss_in;           /* [n_streams][ld] CTCSS branch after its DC blocker (:606) */
+  float *ctcss_power;        /* [n_streams][38] Goertzel powers of the last finished block */
+  long long ld;
+  char *ascii;               /* [n_streams][W] waterfall row, as pmr446_outputs */
+  float *peak;               /* [n_streams][2] */
+} pmr446_rx_outputs;
+
+typedef struct pmr446_receiver pmr446_receiver;
+void pmr446_rx_default_config(pmr446_rx_config *cfg);
+int pmr446_receiver_create(const pmr446_rx_config *cfg, pmr446_receiver **out);
+int pmr446_receiver_destroy(pmr446_receiver *r);
+long long pmr446_receiver_max_ns(const pmr446_receiver *r);
+int pmr446_receiver_execute(pmr446_receiver *r, const void *iq, long long iq_stride, unsigned n, const pmr446_rx_outputs *out,
+                            unsigned *ns);
+int pmr446_receiver_execute_device(pmr446_receiver *r, const void *iq, long long iq_stride, unsigned n, const pmr446_rx_outputs *out,
+                                   unsigned *ns, void *cuda_stream);
+int pmr446_receiver_last_launches(const pmr446_receiver *r);
+/* Back to stream start: scanning, no active channel, all filter state zero. */
+int pmr446_receiver_reset(pmr446_receiver *r);
+
 /* ---- dsd_in chain: single-channel FM demodulator feeding DSD (src/dsd_in.c) ------------------- */
 typedef struct {
   int n_streams;

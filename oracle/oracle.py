@@ -34,6 +34,22 @@ class DsdCfg(C.Structure):
                 ("chunk", C.c_uint), ("dc_alpha", C.c_float), ("resamp_as", C.c_float), ("kf", C.c_float)]
 
 
+class RxCfg(C.Structure):
+    _fields_ = [("chain", PmrCfg), ("squelch_level", C.c_float), ("channel_mask", C.c_ulonglong), ("lock_mode", C.c_int),
+                ("ctcss_block", C.c_uint), ("ctcss_dc_alpha", C.c_float)]
+
+
+class RxStatus(C.Structure):
+    _fields_ = [("state", C.c_int), ("active_chan", C.c_int), ("rssi", C.c_float), ("n_audio", C.c_uint),
+                ("tone_detected", C.c_int), ("ctcss_index", C.c_int), ("ctcss_freq", C.c_float), ("max_power", C.c_float),
+                ("events", C.c_int)]
+
+
+class RxOut(C.Structure):
+    _fields_ = [("rssi", C.c_void_p), ("audio", C.c_void_p), ("pcm", C.c_void_p), ("ctcss_in", C.c_void_p),
+                ("ctcss_power", C.c_void_p), ("chan", C.c_void_p), ("ld", C.c_uint)]
+
+
 class Knobs(C.Structure):
     _fields_ = [("resamp_npfb", C.c_int), ("resamp_fc_mode", C.c_int), ("kaiser_r_mode", C.c_int),
                 ("asgram_avg", C.c_int), ("asgram_keep_buf", C.c_int)]
@@ -41,7 +57,7 @@ class Knobs(C.Structure):
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle_pmr446.so")
-    srcs = [os.path.join(_HERE, f) for f in ("liquid_subset.c", "chains.c", "liquid_subset.h", "chains.h", "resamp_tmpl.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("liquid_subset.c", "chains.c", "receiver.c", "liquid_subset.h", "chains.h", "receiver.h", "resamp_tmpl.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
@@ -58,6 +74,12 @@ def lib():
         L.oracle_pmr_res_size.argtypes = [C.c_void_p]
         L.oracle_pmr_chan_size.argtypes = [C.c_void_p]
         L.oracle_pmr_execute.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.POINTER(PmrOut), C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
+        L.oracle_rx_default_cfg.argtypes = [C.POINTER(RxCfg)]
+        L.oracle_rx_create.restype = C.c_void_p
+        L.oracle_rx_create.argtypes = [C.POINTER(RxCfg)]
+        L.oracle_rx_destroy.argtypes = [C.c_void_p]
+        L.oracle_rx_chan_size.argtypes = [C.c_void_p]
+        L.oracle_rx_execute.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.POINTER(RxOut), C.POINTER(RxStatus), C.POINTER(C.c_uint)]
         L.oracle_dsd_create.restype = C.c_void_p
         L.oracle_dsd_create.argtypes = [C.POINTER(DsdCfg)]
         L.oracle_dsd_destroy.argtypes = [C.c_void_p]
@@ -218,6 +240,66 @@ class PmrOracle:
             else:
                 r[k] = np.concatenate([p[k] for p in parts], axis=-1)
         return r
+
+
+class RxOracle:
+    """One stream of the reference receiver: RSSI, squelch/selector state machine, the selected channel's
+    demodulation chain and the CTCSS detector (src/sdr_pmr446.c:828-908; oracle/receiver.c)."""
+
+    STATUS_FIELDS = ("state", "active_chan", "rssi", "n_audio", "tone_detected", "ctcss_index", "ctcss_freq", "max_power", "events")
+
+    def __init__(self, squelch_level=18.0, channel_mask=2 ** 64 - 1, lock_mode=0, ctcss_block=2441, **chain_kw):
+        self.cfg = RxCfg()
+        lib().oracle_rx_default_cfg(C.byref(self.cfg))
+        for k, v in chain_kw.items():
+            if not hasattr(self.cfg.chain, k):
+                raise AttributeError(k)
+            setattr(self.cfg.chain, k, v)
+        self.cfg.squelch_level = squelch_level
+        self.cfg.channel_mask = channel_mask
+        self.cfg.lock_mode = lock_mode
+        self.cfg.ctcss_block = ctcss_block
+        self.h = lib().oracle_rx_create(C.byref(self.cfg))
+        if not self.h:
+            raise RuntimeError("oracle_rx_create failed")
+        self.M = self.cfg.chain.num_channels
+        self.chan_size = lib().oracle_rx_chan_size(self.h)
+
+    def close(self):
+        if self.h:
+            lib().oracle_rx_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def execute(self, iq):
+        """One chunk -> dict(status fields, rssi_ch [M], audio, pcm, ctcss_in [n_audio], ctcss_power [38], ns)."""
+        iq = np.ascontiguousarray(iq)
+        n = iq.shape[0] // 2 if self.cfg.chain.in_fmt == FMT_CU8 else iq.shape[0]
+        ld = self.chan_size
+        bufs = {"rssi": np.zeros(self.M, np.float32), "audio": np.zeros(ld, np.float32), "pcm": np.zeros(ld, np.int16),
+                "ctcss_in": np.zeros(ld, np.float32), "ctcss_power": np.zeros(38, np.float32)}
+        out = RxOut()
+        out.ld = ld
+        for k, v in bufs.items():
+            setattr(out, k, v.ctypes.data)
+        st, ns = RxStatus(), C.c_uint(0)
+        rc = lib().oracle_rx_execute(self.h, _p(iq), n, C.byref(out), C.byref(st), C.byref(ns))
+        if rc:
+            raise RuntimeError("oracle_rx_execute rc=%d" % rc)
+        r = {k: getattr(st, k) for k in self.STATUS_FIELDS}
+        r["ns"] = ns.value
+        r["rssi_ch"] = bufs["rssi"]
+        r["ctcss_power"] = bufs["ctcss_power"]
+        for k in ("audio", "pcm", "ctcss_in"):
+            r[k] = bufs[k][:st.n_audio]
+        return r
+
+    def run(self, iq, chunk=None):
+        """Whole capture in chunks -> list of per-chunk dicts."""
+        chunk = chunk or self.cfg.chain.chunk
+        step = 2 * chunk if self.cfg.chain.in_fmt == FMT_CU8 else chunk
+        return [self.execute(iq[o:o + step]) for o in range(0, iq.shape[0], step)]
 
 
 class DsdOracle:

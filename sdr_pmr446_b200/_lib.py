@@ -32,6 +32,26 @@ class Outputs(C.Structure):
                 ("ascii", C.c_void_p), ("peak", C.c_void_p), ("psd", C.c_void_p)]
 
 
+class RxConfig(C.Structure):
+    """pmr446_rx_config (include/pmr446_b200.h)."""
+    _fields_ = [("chain", Config), ("squelch_level", C.c_float), ("channel_mask", C.c_ulonglong), ("lock_mode", C.c_int),
+                ("ctcss_block", C.c_uint), ("ctcss_dc_alpha", C.c_float)]
+
+
+class RxStatus(C.Structure):
+    """pmr446_rx_status (include/pmr446_b200.h)."""
+    _fields_ = [("state", C.c_int), ("active_chan", C.c_int), ("rssi", C.c_float), ("n_audio", C.c_uint),
+                ("tone_detected", C.c_int), ("ctcss_index", C.c_int), ("ctcss_freq", C.c_float), ("max_power", C.c_float),
+                ("events", C.c_int)]
+
+
+class RxOutputs(C.Structure):
+    """pmr446_rx_outputs (include/pmr446_b200.h)."""
+    _fields_ = [("rssi", C.c_void_p), ("status", C.c_void_p), ("audio", C.c_void_p), ("pcm", C.c_void_p),
+                ("ctcss_in", C.c_void_p), ("ctcss_power", C.c_void_p), ("ld", C.c_longlong), ("ascii", C.c_void_p),
+                ("peak", C.c_void_p)]
+
+
 class DsdConfig(C.Structure):
     """dsd446_config (include/pmr446_b200.h)."""
     _fields_ = [("n_streams", C.c_int), ("device", C.c_int), ("fs_in", C.c_uint), ("in_fmt", C.c_int),
@@ -49,6 +69,8 @@ EXPORTS = [
     "pmr446_batch_max_ns", "pmr446_batch_execute", "pmr446_batch_execute_device", "pmr446_batch_last_launches",
     "pmr446_batch_reset", "pmr446_last_error", "pmr446_measure_fp32_peak", "pmr446_batch_timing",
     "pmr446_batch_get_timings",
+    "pmr446_rx_default_config", "pmr446_receiver_create", "pmr446_receiver_destroy", "pmr446_receiver_max_ns",
+    "pmr446_receiver_execute", "pmr446_receiver_execute_device", "pmr446_receiver_last_launches", "pmr446_receiver_reset",
     "dsd446_default_config", "dsd446_batch_create", "dsd446_batch_destroy", "dsd446_batch_max_res",
     "dsd446_batch_max_out", "dsd446_batch_execute", "dsd446_batch_execute_device", "dsd446_batch_reset",
     "pmr446_design_msresamp", "pmr446_design_pfbch", "pmr446_design_asgram_window", "pmr446_design_nco_dtheta",
@@ -90,6 +112,17 @@ def lib():
         L.pmr446_measure_fp32_peak.argtypes = [C.POINTER(C.c_double), C.c_void_p]
         L.pmr446_batch_timing.argtypes = [C.c_void_p, C.c_int]
         L.pmr446_batch_get_timings.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]
+        L.pmr446_rx_default_config.argtypes = [C.POINTER(RxConfig)]
+        L.pmr446_rx_default_config.restype = None
+        L.pmr446_receiver_create.argtypes = [C.POINTER(RxConfig), C.POINTER(C.c_void_p)]
+        L.pmr446_receiver_destroy.argtypes = [C.c_void_p]
+        L.pmr446_receiver_max_ns.argtypes = [C.c_void_p]
+        L.pmr446_receiver_max_ns.restype = C.c_longlong
+        L.pmr446_receiver_execute.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_uint, C.POINTER(RxOutputs), C.POINTER(C.c_uint)]
+        L.pmr446_receiver_execute_device.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_uint, C.POINTER(RxOutputs),
+                                                     C.POINTER(C.c_uint), C.c_void_p]
+        L.pmr446_receiver_last_launches.argtypes = [C.c_void_p]
+        L.pmr446_receiver_reset.argtypes = [C.c_void_p]
         L.dsd446_default_config.argtypes = [C.POINTER(DsdConfig)]
         L.dsd446_default_config.restype = None
         L.dsd446_batch_create.argtypes = [C.POINTER(DsdConfig), C.POINTER(C.c_void_p)]

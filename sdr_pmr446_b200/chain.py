@@ -151,6 +151,84 @@ class PmrBatch:
         return ny.value, ns.value
 
 
+class PmrReceiver:
+    """n_streams reference receivers: RSSI, squelch / selector, selected-channel audio, CTCSS detector
+    (/root/reference/src/sdr_pmr446.c:828-908).  Keyword arguments not named below configure the DSP chain."""
+
+    STATUS_FIELDS = ("state", "active_chan", "rssi", "n_audio", "tone_detected", "ctcss_index", "ctcss_freq", "max_power", "events")
+
+    def __init__(self, squelch_level=18.0, channel_mask=2 ** 64 - 1, lock_mode=0, ctcss_block=2441, **chain_kw):
+        self.cfg = _lib.RxConfig()
+        lib().pmr446_rx_default_config(C.byref(self.cfg))
+        for k, v in chain_kw.items():
+            if not hasattr(self.cfg.chain, k):
+                raise AttributeError("pmr446_config has no field %r" % k)
+            setattr(self.cfg.chain, k, v)
+        self.cfg.squelch_level = squelch_level
+        self.cfg.channel_mask = channel_mask
+        self.cfg.lock_mode = lock_mode
+        self.cfg.ctcss_block = ctcss_block
+        h = C.c_void_p()
+        check(lib().pmr446_receiver_create(C.byref(self.cfg), C.byref(h)), "pmr446_receiver_create")
+        self.h = h
+        self.S = self.cfg.chain.n_streams
+        self.M = self.cfg.chain.num_channels
+        self.max_ns = lib().pmr446_receiver_max_ns(self.h)
+
+    def close(self):
+        if getattr(self, "h", None) and lib is not None:
+            try:
+                lib().pmr446_receiver_destroy(self.h)
+            except TypeError:  # interpreter shutdown
+                pass
+            self.h = None
+
+    __del__ = close
+
+    def reset(self):
+        check(lib().pmr446_receiver_reset(self.h), "pmr446_receiver_reset")
+
+    @property
+    def last_launches(self):
+        return lib().pmr446_receiver_last_launches(self.h)
+
+    def execute(self, iq):
+        """One chunk of every stream (host buffers).  Returns dict: status fields as [S] arrays, rssi_ch [S, M],
+        audio / pcm / ctcss_in [S, ns] (valid for stream s up to n_audio[s]), ctcss_power [S, 38], ns."""
+        iq = np.ascontiguousarray(iq)
+        if iq.ndim == 1:
+            iq = iq[None, :]
+        assert iq.shape[0] == self.S
+        n = iq.shape[1] // 2 if self.cfg.chain.in_fmt == FMT_CU8 else iq.shape[1]
+        S, M, ld = self.S, self.M, self.max_ns
+        status = (_lib.RxStatus * S)()
+        bufs = {"rssi": np.zeros((S, M), np.float32), "audio": np.zeros((S, ld), np.float32), "pcm": np.zeros((S, ld), np.int16),
+                "ctcss_in": np.zeros((S, ld), np.float32), "ctcss_power": np.zeros((S, 38), np.float32)}
+        out = _lib.RxOutputs()
+        out.ld = ld
+        out.status = C.addressof(status)
+        for k, v in bufs.items():
+            setattr(out, k, v.ctypes.data)
+        ns = C.c_uint(0)
+        check(lib().pmr446_receiver_execute(self.h, iq.ctypes.data, iq.strides[0], n, C.byref(out), C.byref(ns)),
+              "pmr446_receiver_execute")
+        r = {k: np.array([getattr(status[s], k) for s in range(S)]) for k in self.STATUS_FIELDS}
+        r["ns"] = ns.value
+        r["rssi_ch"] = bufs["rssi"]
+        r["ctcss_power"] = bufs["ctcss_power"]
+        for k in ("audio", "pcm", "ctcss_in"):
+            r[k] = bufs[k][:, :ns.value]
+        return r
+
+    def run(self, iq, chunk=None):
+        """Whole capture in chunks -> list of per-chunk dicts."""
+        chunk = chunk or self.cfg.chain.max_chunk
+        if iq.ndim == 1:
+            iq = iq[None, :]
+        step = 2 * chunk if self.cfg.chain.in_fmt == FMT_CU8 else chunk
+        return [self.execute(iq[:, o:o + step]) for o in range(0, iq.shape[1], step)]
+
+
 def dsd_default_config(**kw):
     cfg = _lib.DsdConfig()
     lib().dsd446_default_config(C.byref(cfg))

@@ -21,6 +21,8 @@ struct AudioParams {
   int tiles;               // tiles per row
   long long tile0;         // tile k covers outputs [k*own, (k+1)*own), own = AU_SPAN - lead
   long long f0, f1;        // owned samples
+  const long long* row_range;   // optional [rows][2]: per-row {f0, f1} (device memory) replacing f0/f1/tile0 -- the
+                           // squelch-selected stream of the receiver advances at a different pace per stream
   int lead;                // lead-in outputs per tile (multiple of 16; 16 without, 128 with the low-pass)
   const float* hp_taps;    // [HP_PAD] zero-padded to a multiple of 16
   int hp_chunks;           // HP_PAD / 16
@@ -33,6 +35,7 @@ struct AudioParams {
   short* pcm;              // optional [rows][out_ld]
   float* lpcomp;           // optional [rows][out_ld]
   long long out_ld;
+  long long lpcomp_ld;     // row stride of lpcomp; 0 = out_ld
 };
 
 constexpr int AU_THREADS = 128;
@@ -81,7 +84,7 @@ __device__ __forceinline__ void fir16(const float* __restrict__ xs, const float*
   if (kb < chunks) step(wa, wb, kb);
 }
 
-__global__ void __launch_bounds__(AU_THREADS) audio_kernel(AudioParams p) {
+static __global__ void __launch_bounds__(AU_THREADS) audio_kernel(AudioParams p) {
   extern __shared__ float smem[];
   // layout: xs[padidx(AU_MAXHALO + AU_SPAN + 16)] input tile; ys[...] second buffer (gain*hp, then de-emph)
   constexpr int XN = AU_MAXHALO + AU_SPAN + 16;
@@ -92,12 +95,18 @@ __global__ void __launch_bounds__(AU_THREADS) audio_kernel(AudioParams p) {
 
   const int row = blockIdx.x / p.tiles;
   const int lead = p.lead, own = AU_SPAN - lead;
-  const long long tile = p.tile0 + blockIdx.x % p.tiles;
+  long long pf0 = p.f0, pf1 = p.f1, tile = p.tile0 + blockIdx.x % p.tiles;
+  if (p.row_range) {
+    pf0 = p.row_range[2 * row];
+    pf1 = p.row_range[2 * row + 1];
+    tile = pf0 / own + blockIdx.x % p.tiles;
+    if (tile * own >= pf1) return;   // block-uniform
+  }
   const long long o0 = tile * own - lead;   // absolute index of computed output 0 (multiple of 16)
   const float* drow = p.demod + (long long)row * p.demod_stride;
   const int t = threadIdx.x;
   // everything below is 32-bit and relative to o0
-  const long long lo64 = p.f0 - o0, hi64 = p.f1 - o0;
+  const long long lo64 = pf0 - o0, hi64 = pf1 - o0;
   const int f0r = (int)(lo64 < -(1 << 28) ? -(1 << 28) : lo64);                 // first owned output, relative
   const int f1r = (int)(hi64 > (1 << 28) ? (1 << 28) : hi64);                   // one past the last available input/output
   const int z0r = (int)(-o0 > (1 << 28) ? (1 << 28) : (-o0 < -(1 << 28) ? -(1 << 28) : -o0));   // stream start, relative
@@ -141,7 +150,7 @@ __global__ void __launch_bounds__(AU_THREADS) audio_kernel(AudioParams p) {
   const bool own_thread = (ob >= lead);
   // complementary low-pass branch (A.11): delayed input minus high-pass output
   if (p.lpcomp && own_thread && need) {
-    float* lrow = p.lpcomp + (long long)row * p.out_ld;
+    float* lrow = p.lpcomp + (long long)row * (p.lpcomp_ld ? p.lpcomp_ld : p.out_ld);
 #pragma unroll
     for (int r = 0; r < 16; r++) {
       const int f = ob + r;

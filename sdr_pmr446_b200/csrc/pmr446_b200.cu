@@ -337,6 +337,8 @@ extern "C" int pmr446_batch_execute_device(pmr446_batch* b, const void* iq, long
       ap.tiles = (int)((f1 + own - 1) / own - ap.tile0);
       ap.f0 = f0;
       ap.f1 = f1;
+      ap.row_range = nullptr;
+      ap.lpcomp_ld = 0;
       ap.hp_taps = (const float*)b->d_hp.p;
       ap.hp_chunks = b->hp_chunks;
       ap.hp_delay = b->hp_delay;

@@ -9,7 +9,7 @@ inverse of the SoapyRTLSDR conversion (u8 - 127.4)/128.
 All phases are closed-form in the absolute sample index, so a capture generated in pieces
 (`start=`) is identical to one generated in one go (noise aside, which is drawn per call).
 """
-from dataclasses import dataclass, field
+from dataclasses import dataclass, field, replace
 from typing import Sequence
 
 import numpy as np
@@ -26,6 +26,8 @@ class Carrier:
     audio_dev_hz: float = 2500.0
     ctcss_dev_hz: float = 500.0
     phase0: float = 0.0
+    t_on: float = 0.0       # the carrier is keyed on during [t_on, t_off) seconds (squelch / selector tests)
+    t_off: float = float("inf")
 
 
 @dataclass
@@ -49,8 +51,7 @@ CFG1_CARRIERS = (
 def rotated_carriers(stream_id: int, num_channels: int = 16, base=CFG1_CARRIERS):
     """cfg3/cfg5: channel set rotated by stream_id mod M."""
     r = stream_id % num_channels
-    return tuple(Carrier(((c.channel - 1 + r) % num_channels) + 1, c.amplitude, c.audio_hz, c.ctcss_hz,
-                         c.audio_dev_hz, c.ctcss_dev_hz, c.phase0) for c in base)
+    return tuple(replace(c, channel=((c.channel - 1 + r) % num_channels) + 1) for c in base)
 
 
 def channel_offset_hz(channel_1based: int, num_channels: int = 16) -> float:
@@ -69,7 +70,10 @@ def make_cf64(spec: CaptureSpec, n: int, seed: int = 446, start: int = 0) -> np.
             ph -= (c.audio_dev_hz / c.audio_hz) * np.cos(2.0 * np.pi * c.audio_hz * t)
         if c.ctcss_hz > 0:
             ph -= (c.ctcss_dev_hz / c.ctcss_hz) * np.cos(2.0 * np.pi * c.ctcss_hz * t)
-        x += c.amplitude * np.exp(1j * ph)
+        keyed = c.amplitude * np.exp(1j * ph)
+        if c.t_on > 0.0 or c.t_off != float("inf"):
+            keyed = np.where((t >= c.t_on) & (t < c.t_off), keyed, 0.0)
+        x += keyed
     if spec.noise_sigma > 0:
         rng = np.random.Generator(np.random.PCG64(seed))
         x += spec.noise_sigma * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
