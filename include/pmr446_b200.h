@@ -226,6 +226,11 @@ unsigned pmr446_design_nco_dtheta(float dtheta);
 long long pmr446_count_resampled(float rate, float as, long long n_in);
 
 const char *pmr446_last_error(void);
+/* Page-locked host buffers for the host-buffer calls: captures read into them (file, SDR driver, socket) reach the
+ * GPU at full PCIe rate and let the time-sliced copy in pmr446_batch_execute() overlap the kernels.  Replaces the
+ * reference's stack arrays (src/sdr_pmr446.c:738-745). */
+int pmr446_host_alloc(void **ptr, unsigned long long bytes);
+int pmr446_host_free(void *ptr);
 /* Measures the FP32 FFMA issue peak of the current device (TFLOP/s) with a register-only
  * kernel; used as the roofline denominator by bench.py. */
 int pmr446_measure_fp32_peak(double *tflops, void *cuda_stream);

@@ -67,7 +67,7 @@ class DsdOutputs(C.Structure):
 EXPORTS = [
     "pmr446_default_config", "pmr446_batch_create", "pmr446_batch_destroy", "pmr446_batch_max_res",
     "pmr446_batch_max_ns", "pmr446_batch_execute", "pmr446_batch_execute_device", "pmr446_batch_last_launches",
-    "pmr446_batch_reset", "pmr446_last_error", "pmr446_measure_fp32_peak", "pmr446_batch_timing",
+    "pmr446_batch_reset", "pmr446_last_error", "pmr446_host_alloc", "pmr446_host_free", "pmr446_measure_fp32_peak", "pmr446_batch_timing",
     "pmr446_batch_get_timings",
     "pmr446_rx_default_config", "pmr446_receiver_create", "pmr446_receiver_destroy", "pmr446_receiver_max_ns",
     "pmr446_receiver_execute", "pmr446_receiver_execute_device", "pmr446_receiver_last_launches", "pmr446_receiver_reset",
@@ -109,6 +109,8 @@ def lib():
         L.pmr446_batch_last_launches.argtypes = [C.c_void_p]
         L.pmr446_batch_reset.argtypes = [C.c_void_p]
         L.pmr446_last_error.restype = C.c_char_p
+        L.pmr446_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_ulonglong]
+        L.pmr446_host_free.argtypes = [C.c_void_p]
         L.pmr446_measure_fp32_peak.argtypes = [C.POINTER(C.c_double), C.c_void_p]
         L.pmr446_batch_timing.argtypes = [C.c_void_p, C.c_int]
         L.pmr446_batch_get_timings.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]

@@ -515,6 +515,23 @@ extern "C" int pmr446_measure_fp32_peak(double* tflops, void* cuda_stream) {
 
 extern "C" const char* pmr446_last_error(void) { return pmr::last_error_string().c_str(); }
 
+extern "C" int pmr446_host_alloc(void** ptr, unsigned long long bytes) {
+  if (!ptr) return fail(PMR446_EINVAL, "null argument");
+  *ptr = nullptr;
+  if (int rc = select_device(-1)) return rc;
+  if (cudaHostAlloc(ptr, bytes ? (size_t)bytes : 16, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    *ptr = nullptr;
+    return fail(PMR446_ENOMEM, "cudaHostAlloc failed");
+  }
+  return PMR446_OK;
+}
+
+extern "C" int pmr446_host_free(void* ptr) {
+  if (ptr) CUDA_TRY(cudaFreeHost(ptr));
+  return PMR446_OK;
+}
+
 // ================================================================================================
 // Host-only introspection of the filter design and the sample-count bookkeeping (no GPU needed).
 // ================================================================================================

@@ -58,3 +58,69 @@ def test_batch_file_harness_all_channels(tmp_path):
             assert g.size == r["pcm"].shape[1]
             d = np.abs(g[500:].astype(np.int32) - r["pcm"][c, 500:].astype(np.int32))
             assert d.max() <= PCM_TOL_LSB, (s, c, int(d.max()))
+
+
+def test_rx_file_harness_wav_and_log(tmp_path):
+    """pmr446_rx_file: the reference program on a capture file -- WAV of the selected channel, the reference's log lines."""
+    import struct
+
+    import rx_scenarios as sc
+    from oracle import oracle as orc
+    _build()
+    car = sc.keyed_two_calls()
+    iq = sc.capture(car, seconds=2.5)
+    cap = tmp_path / "cap.cu8"
+    iq.tofile(cap)
+    wav = tmp_path / "out.wav"
+    p = subprocess.run([os.path.join(ROOT, "host", "pmr446_rx_file"), "-8", "-g", "1.0", "-o", str(wav), str(cap)], check=True,
+                       capture_output=True, text=True)
+    log = p.stderr
+    assert "Tuned to channel 2" in log and "Detuned from channel 2" in log and "Tuned to channel 7" in log
+    assert "Acquired CTCSS code: 1 (frequency: 67.00Hz)" in log and "Acquired CTCSS code: 8 (frequency: 88.50Hz)" in log
+    raw = wav.read_bytes()
+    assert raw[:4] == b"RIFF" and raw[8:16] == b"WAVEfmt " and raw[36:40] == b"data"
+    fmt, ch, rate, _, _, bits = struct.unpack("<HHIIHH", raw[20:36])
+    assert (fmt, ch, rate, bits) == (1, 1, 12500, 16)
+    data_len = struct.unpack("<I", raw[40:44])[0]
+    pcm = np.frombuffer(raw[44:], np.int16)
+    assert data_len == pcm.size * 2 and struct.unpack("<I", raw[4:8])[0] == 36 + data_len
+    o = orc.RxOracle(fs_in=sc.FS, in_fmt=1, chunk=sc.CHUNK, audio_gain=1.0)
+    rows = o.run(iq, sc.CHUNK)
+    o.close()
+    ref = np.concatenate([r["pcm"] for r in rows])
+    assert pcm.size == ref.size
+    # strict on the steady part of the first call (chunks 2..9), see test_gpu_receiver_parity for why
+    a, b = 2 * 1221, 9 * 1220
+    assert np.abs(pcm[a:b].astype(np.int32) - ref[a:b].astype(np.int32)).max() <= PCM_TOL_LSB
+
+
+def test_rx_file_harness_waterfall_footer(tmp_path):
+    import rx_scenarios as sc
+    _build()
+    iq = sc.capture(sc.stronger_later(), seconds=0.6)
+    cap = tmp_path / "cap.cu8"
+    iq.tofile(cap)
+    p = subprocess.run([os.path.join(ROOT, "host", "pmr446_rx_file"), "-8", "-w", "64", "-m", "3,4", "-f", "-o", str(tmp_path / "o.wav"), str(cap)],
+                       check=True, capture_output=True, text=True)
+    rows = [ln for ln in p.stdout.split("\n") if ln.startswith(" > ")]
+    assert len(rows) == 7 and all(len(r.split(" < ")[0]) == 3 + 64 for r in rows)
+    foot = [ln for ln in p.stdout.split("\n") if "MHz" in ln][-1]   # text mode turns the footer's \r into \n
+    assert "^^" in foot and "--" in foot and "446.100 MHz [8]" in foot and " 01 " in foot
+    assert (tmp_path / "o.wav").read_bytes()[20:22] == b"\x03\x00"   # IEEE float WAV
+
+
+def test_dsd_pipe_harness(tmp_path):
+    """dsd446_pipe writes the dsd_in s16 stream to stdout (what `| dsd -i -` reads)."""
+    from oracle import oracle as orc
+    from sdr_pmr446_b200 import synth
+    _build()
+    iq = synth.cfg2_capture(n=1_200_000)
+    cap = tmp_path / "cap.cu8"
+    iq.tofile(cap)
+    with open(cap, "rb") as fi:
+        p = subprocess.run([os.path.join(ROOT, "host", "dsd446_pipe"), "-r", "2400000", "-8", "-"], stdin=fi, check=True, capture_output=True)
+    pcm = np.frombuffer(p.stdout, np.int16)
+    o = orc.DsdOracle(fs_in=2400000, in_fmt=1, chunk=200000)
+    r = o.run(iq, 200000)
+    assert pcm.size == r["pcm"].size == r["nz"]
+    assert np.abs(pcm[200:].astype(np.int32) - r["pcm"][200:].astype(np.int32)).max() <= PCM_TOL_LSB
