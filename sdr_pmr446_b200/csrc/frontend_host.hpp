@@ -12,6 +12,7 @@
 #include "common_host.hpp"
 #include "design.hpp"
 #include "frontend.cuh"
+#include "hbarb_tile.cuh"
 
 namespace pmr {
 
@@ -28,6 +29,8 @@ struct Level {
   float hb[4][20];
   float scale = 1.0f;
   cascade_fn fn = nullptr;
+  bool tile = false;      // last level runs hbarb_tile_kernel<10, 2, 3> instead of the segment-sequential cascade
+  float arb_rows[2][14];
   DevBuf ring;            // output ring [S][cap] float2
   long long cap = 0;
   long long n_in = 0, n_out = 0;   // absolute counts: inputs seen, outputs written
@@ -191,6 +194,18 @@ struct Frontend {
           L.seg_len = (int)std::max<long long>(q, L.seg_len / q * q);
         }
       }
+      if (L.arb && L.src == SRC_RING && L.nst == 1 && L.ms[0] == 10 && plan.step == 3u << 23) {
+        // rate 2/3: the resampler phase has period 2 -> tiled kernel; a call recomputes at most one tile, so the
+        // producer ring must keep (and zir_tail_kernel must fix) that much corrected history
+        L.tile = true;
+        const int th = HT_R / 2 * 3 * HT_THREADS;
+        L.halo = (2 * (th + HT_HH + 19) + L.unit - 1) / L.unit * L.unit;
+        for (int r = 0; r < 2; r++) {
+          const unsigned row = (unsigned)((((unsigned long long)r * plan.step) & ((1u << 24) - 1)) >> (24 - plan.bits));
+          for (int k = 0; k < 14; k++) L.arb_rows[r][k] = plan.pfb[(size_t)row * plan.sub_len + k];
+        }
+        cudaFuncSetAttribute(hbarb_tile_kernel<10, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hbarb_tile_smem<10, 2, 3>());
+      }
       L.max_in = max_in;
       long long max_hb = max_in / L.D + 1;
       L.max_out = L.arb ? (long long)design::arb_outputs_after((uint64_t)max_hb, plan.step) + 2 : max_hb;
@@ -317,7 +332,33 @@ struct Frontend {
         tm->mark(st, TM_DC);
       }
       long long new_out = L.n_out;
-      if (out1 > out0 || (L.dc == DC_ZSR && nseg > 0)) {
+      if (L.tile) {
+        const long long j0 = L.n_out, j1 = out1 > out0 ? (long long)design::arb_outputs_after((uint64_t)out1, plan.step) : L.n_out;
+        if (j1 > j0) {
+          HbArbParams hp;
+          memset(&hp, 0, sizeof hp);
+          hp.ring = (const float2*)sv.cur;
+          hp.ring_stride = levels[l - 1].cap;
+          hp.ring_mask = sv.ring_mask;
+          hp.n1 = lvl_n1;
+          hp.corr = sv.corr;
+          hp.n_streams = S;
+          hp.tile0 = j0 / HT_TJ;
+          hp.tiles = (int)((j1 + HT_TJ - 1) / HT_TJ - hp.tile0);
+          hp.j0 = j0;
+          hp.j1 = j1;
+          hp.scale = L.scale;
+          memcpy(hp.hb, L.hb[0], sizeof hp.hb);
+          memcpy(hp.arb, L.arb_rows, sizeof hp.arb);
+          hp.dst = (float2*)L.ring.p;
+          hp.dst_stride = L.cap;
+          hp.dst_mask = L.cap - 1;
+          hbarb_tile_kernel<10, 2, 3><<<(unsigned)((long long)S * hp.tiles), HT_THREADS, hbarb_tile_smem<10, 2, 3>(), st>>>(hp);
+          *launches += 1;
+          tm->mark(st, TM_CASCADE0 + (int)std::min<size_t>(l, 2));
+          new_out = j1;
+        }
+      } else if (out1 > out0 || (L.dc == DC_ZSR && nseg > 0)) {
         CascadeParams cp;
         memset(&cp, 0, sizeof cp);
         cp.src = sv;
