@@ -115,7 +115,11 @@ __device__ __forceinline__ void stg256(void* p, const float* f) {
 template <int SRC>
 struct Loader;
 
-__device__ __forceinline__ float u8f(unsigned w, int k) { return (float)((w >> (8 * k)) & 0xffu); }
+// byte k of w as a float, exactly: one PRMT drops the byte into the mantissa of 2^23 (0x4B000000), one FADD removes
+// the 2^23 -- both on the ALU/FMA pipes instead of the quarter-rate I2F conversion unit
+__device__ __forceinline__ float u8f(unsigned w, int k) {
+  return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + (unsigned)k)) - 8388608.0f;
+}
 
 // ---- cu8 two-source --------------------------------------------------------------------
 template <>

@@ -15,6 +15,7 @@
 
 #include "../../include/pmr446_b200.h"
 #include "../../include/pmr446_taps.h"
+#include "audio_fft.cuh"
 #include "backend.cuh"
 #include "channelizer.cuh"
 #include "channelizer_generic.cuh"
@@ -47,6 +48,8 @@ struct pmr446_batch {
   // audio
   DevBuf d_hp, d_lp;
   int hp_chunks = 0, lp_chunks = 0, hp_delay = 0;
+  bool fft_audio = false;    // audio / pcm by fast convolution (audio_fft_kernel); the direct-form kernel serves lpcomp
+  DevBuf d_resp, d_aftw;
   // waterfall
   Waterfall wf;
   // staging for the host-buffer call
@@ -148,7 +151,7 @@ extern "C" int pmr446_batch_create(const pmr446_config* cfg, pmr446_batch** out)
   }
 
   // demod ring: history for the audio FIR halo + one chunk
-  b->demod_cap = next_pow2(b->max_ns + AU_MAXHALO + AU_LEAD_LP + 64);
+  b->demod_cap = next_pow2(b->max_ns + std::max(AU_MAXHALO + AU_LEAD_LP, AF_N) + 64);
   if ((rc = b->d_demod.alloc_zero((size_t)S * M * b->demod_cap * sizeof(float)))) { pmr446_batch_destroy(b); return rc; }
 
   // audio filters
@@ -165,6 +168,48 @@ extern "C" int pmr446_batch_create(const pmr446_config* cfg, pmr446_batch** out)
   if ((rc = upload_padded_taps(hpt, hpn, b->d_hp, &b->hp_chunks)) || (rc = upload_padded_taps(lpt, lpn, b->d_lp, &b->lp_chunks))) {
     pmr446_batch_destroy(b);
     return rc;
+  }
+  // fast-convolution response: hp (x gain) * de-emphasis * optional low-pass, as one impulse response < AF_HALO
+  {
+    const unsigned fir_len = hpn + (cfg->lowpass ? lpn - 1 : 0);
+    const double a1 = cfg->deemph_a1;
+    if (fir_len + 24 <= (unsigned)AF_HALO && fabs(a1) < 0.1) {
+      std::vector<double> h(hpt, hpt + hpn);
+      for (auto& x : h) x *= (double)cfg->audio_gain;
+      // de-emphasis (A.1): y[n] = b0 x[n] + b1 x[n-1] - a1 y[n-1]
+      std::vector<double> de(24);
+      de[0] = cfg->deemph_b0;
+      de[1] = (double)cfg->deemph_b1 - a1 * de[0];
+      for (size_t n = 2; n < de.size(); n++) de[n] = -a1 * de[n - 1];
+      auto conv = [](const std::vector<double>& x, const std::vector<double>& y) {
+        std::vector<double> z(x.size() + y.size() - 1, 0.0);
+        for (size_t i = 0; i < x.size(); i++)
+          for (size_t j = 0; j < y.size(); j++) z[i + j] += x[i] * y[j];
+        return z;
+      };
+      h = conv(h, de);
+      if (cfg->lowpass) h = conv(h, std::vector<double>(lpt, lpt + lpn));
+      std::vector<float2> resp(AF_N), tw(AF_N);
+      for (int k = 0; k < AF_N; k++) {
+        const double a = -2.0 * M_PI * (double)k / (double)AF_N;
+        tw[k] = make_float2((float)cos(a), (float)sin(a));
+      }
+      for (int k0 = 0; k0 < 16; k0++)
+        for (int t = 0; t < 256; t++) {
+          const int k = (t >> 4) + 16 * (t & 15) + 256 * k0;
+          double re = 0.0, im = 0.0;
+          for (size_t n = 0; n < h.size(); n++) {
+            const double a = -2.0 * M_PI * (double)(((long long)k * (long long)n) % AF_N) / (double)AF_N;
+            re += h[n] * cos(a);
+            im += h[n] * sin(a);
+          }
+          resp[k0 * 256 + t] = make_float2((float)(re / AF_N), (float)(im / AF_N));
+        }
+      if ((rc = b->d_resp.alloc(AF_N * sizeof(float2))) || (rc = b->d_aftw.alloc(AF_N * sizeof(float2)))) { pmr446_batch_destroy(b); return rc; }
+      cudaMemcpy(b->d_resp.p, resp.data(), AF_N * sizeof(float2), cudaMemcpyHostToDevice);
+      cudaMemcpy(b->d_aftw.p, tw.data(), AF_N * sizeof(float2), cudaMemcpyHostToDevice);
+      b->fft_audio = true;
+    }
   }
   if (cfg->waterfall > 0) {
     if ((rc = b->wf.init(S, cfg->waterfall))) { pmr446_batch_destroy(b); return rc; }
@@ -325,7 +370,27 @@ extern "C" int pmr446_batch_execute_device(pmr446_batch* b, const void* iq, long
       b->timer.mark(st, TM_GATHER);
     }
     // ---- audio chain ------------------------------------------------------------------------
-    if (out->audio || out->pcm || out->lpcomp) {
+    const bool fft_now = b->fft_audio && (out->audio || out->pcm);
+    if (fft_now) {
+      AudioFftParams fp;
+      fp.demod = (const float*)b->d_demod.p;
+      fp.demod_stride = b->demod_cap;
+      fp.demod_mask = b->demod_cap - 1;
+      fp.rows = S * M;
+      fp.tile0 = f0 / AF_OWN;
+      fp.tiles = (int)((f1 + AF_OWN - 1) / AF_OWN - fp.tile0);
+      fp.f0 = f0;
+      fp.f1 = f1;
+      fp.resp = (const float2*)b->d_resp.p;
+      fp.tw = (const float2*)b->d_aftw.p;
+      fp.audio = out->audio;
+      fp.pcm = out->pcm;
+      fp.out_ld = out->ld;
+      audio_fft_kernel<<<(unsigned)((long long)((fp.rows + 1) / 2) * fp.tiles), AF_T, 0, st>>>(fp);
+      b->launches++;
+      b->timer.mark(st, TM_AUDIO);
+    }
+    if (fft_now ? out->lpcomp != nullptr : (out->audio || out->pcm || out->lpcomp)) {
       AudioParams ap;
       ap.demod = (const float*)b->d_demod.p;
       ap.demod_stride = b->demod_cap;
@@ -348,8 +413,8 @@ extern "C" int pmr446_batch_execute_device(pmr446_batch* b, const void* iq, long
       ap.de_b0 = b->cfg.deemph_b0;
       ap.de_b1 = b->cfg.deemph_b1;
       ap.de_a1 = b->cfg.deemph_a1;
-      ap.audio = out->audio;
-      ap.pcm = out->pcm;
+      ap.audio = fft_now ? nullptr : out->audio;
+      ap.pcm = fft_now ? nullptr : out->pcm;
       ap.lpcomp = out->lpcomp;
       ap.out_ld = out->ld;
       audio_kernel<<<(unsigned)((long long)ap.rows * ap.tiles), AU_THREADS, audio_smem_bytes(), st>>>(ap);
