@@ -87,6 +87,26 @@ __device__ __forceinline__ void dft16(float2* v) {
   for (int q1 = 0; q1 < 4; q1++) dft4<INV>(v[4 * q1], v[4 * q1 + 1], v[4 * q1 + 2], v[4 * q1 + 3]);
 }
 
+// v[af_dig(k)] *= w^k (or conj(w)^k), k = 1..15, with the powers built by a depth-4 product tree: one table load per
+// thread and pass instead of fifteen scattered ones (the table gathers saturated the L1 pipe)
+template <bool CONJ>
+__device__ __forceinline__ void twiddle_powers(float2* v, float2 w) {
+  if (CONJ) w.y = -w.y;
+  float2 pw[16];
+  pw[1] = w;
+  pw[2] = cmul(w, w);
+  pw[3] = cmul(pw[2], w);
+  pw[4] = cmul(pw[2], pw[2]);
+  pw[5] = cmul(pw[4], w);
+  pw[6] = cmul(pw[4], pw[2]);
+  pw[7] = cmul(pw[4], pw[3]);
+  pw[8] = cmul(pw[4], pw[4]);
+#pragma unroll
+  for (int k = 9; k < 16; k++) pw[k] = cmul(pw[8], pw[k - 8]);
+#pragma unroll
+  for (int k = 1; k < 16; k++) v[af_dig(k)] = cmul(v[af_dig(k)], pw[k]);
+}
+
 __global__ void __launch_bounds__(AF_T, 2) audio_fft_kernel(AudioFftParams p) {
   __shared__ float2 sm[AF_SMEM];
   const int t = threadIdx.x;
@@ -105,23 +125,30 @@ __global__ void __launch_bounds__(AF_T, 2) audio_fft_kernel(AudioFftParams p) {
 
   float2 v[16], w[16];
   // thread t holds tile samples t + 256 m: row1 in .x, row2 in .y
+  if (z0 == 0 && z1 >= AF_N && has2) {   // block-uniform: the whole tile exists
 #pragma unroll
-  for (int m = 0; m < 16; m++) {
-    const int i = t + 256 * m;
-    float a = 0.0f, b = 0.0f;
-    if (i >= z0 && i < z1) {
-      const unsigned idx = (base32 + (unsigned)i) & dmask;
-      a = d1[idx];
-      if (has2) b = d2[idx];
+    for (int m = 0; m < 16; m++) {
+      const unsigned idx = (base32 + (unsigned)(t + 256 * m)) & dmask;
+      v[m] = make_float2(d1[idx], d2[idx]);
     }
-    v[m] = make_float2(a, b);
+  } else {
+#pragma unroll
+    for (int m = 0; m < 16; m++) {
+      const int i = t + 256 * m;
+      float a = 0.0f, b = 0.0f;
+      if (i >= z0 && i < z1) {
+        const unsigned idx = (base32 + (unsigned)i) & dmask;
+        a = d1[idx];
+        if (has2) b = d2[idx];
+      }
+      v[m] = make_float2(a, b);
+    }
   }
   const int hi4 = t >> 4, lo4 = t & 15;
 
   // ---- forward: over m (-> k2), twiddle W^(t k2) ----
   dft16<false>(v);
-#pragma unroll
-  for (int k2 = 1; k2 < 16; k2++) v[af_dig(k2)] = cmul(v[af_dig(k2)], __ldg(p.tw + ((t * k2) & (AF_N - 1))));
+  twiddle_powers<false>(v, __ldg(p.tw + t));
 #pragma unroll
   for (int k2 = 0; k2 < 16; k2++) sm[k2 * 256 + t] = v[af_dig(k2)];
   __syncthreads();
@@ -129,8 +156,7 @@ __global__ void __launch_bounds__(AF_T, 2) audio_fft_kernel(AudioFftParams p) {
 #pragma unroll
   for (int m = 0; m < 16; m++) w[m] = sm[hi4 * 256 + lo4 + 16 * m];
   dft16<false>(w);
-#pragma unroll
-  for (int k1 = 1; k1 < 16; k1++) w[af_dig(k1)] = cmul(w[af_dig(k1)], __ldg(p.tw + ((16 * lo4 * k1) & (AF_N - 1))));
+  twiddle_powers<false>(w, __ldg(p.tw + 16 * lo4));
   __syncthreads();
 #pragma unroll
   for (int k1 = 0; k1 < 16; k1++) sm[hi4 * 272 + k1 * 17 + lo4] = w[af_dig(k1)];
@@ -144,26 +170,19 @@ __global__ void __launch_bounds__(AF_T, 2) audio_fft_kernel(AudioFftParams p) {
 #pragma unroll
   for (int k0 = 0; k0 < 16; k0++) w[k0] = cmul(v[af_dig(k0)], __ldg(p.resp + k0 * 256 + t));
 
-  // ---- inverse: over k0 (-> a), twiddle conj W^(16 a k1) ----
+  // ---- inverse: over k0 (-> a), twiddle conj W^(a (16 k1 + k2)): the factor conj W^(a k2) belongs to the next pass
+  // but only depends on this thread's k2 and the register index a, so it rides along here ----
   dft16<true>(w);
-#pragma unroll
-  for (int a = 1; a < 16; a++) {
-    const float2 tw = __ldg(p.tw + ((16 * a * lo4) & (AF_N - 1)));
-    w[af_dig(a)] = cmul(w[af_dig(a)], make_float2(tw.x, -tw.y));
-  }
+  twiddle_powers<true>(w, __ldg(p.tw + 16 * lo4 + hi4));
   __syncthreads();
 #pragma unroll
   for (int a = 0; a < 16; a++) sm[hi4 * 272 + lo4 * 17 + a] = w[af_dig(a)];
   __syncthreads();
-  // thread (k2 = hi4, a = lo4): over k1 (-> b), twiddle conj W^((a + 16 b) k2)
+  // thread (k2 = hi4, a = lo4): over k1 (-> b), twiddle conj W^(16 b k2)
 #pragma unroll
   for (int k1 = 0; k1 < 16; k1++) v[k1] = sm[hi4 * 272 + k1 * 17 + lo4];
   dft16<true>(v);
-#pragma unroll
-  for (int b = 0; b < 16; b++) {
-    const float2 tw = __ldg(p.tw + (((lo4 + 16 * b) * hi4) & (AF_N - 1)));
-    v[af_dig(b)] = cmul(v[af_dig(b)], make_float2(tw.x, -tw.y));
-  }
+  twiddle_powers<true>(v, __ldg(p.tw + 16 * hi4));
   __syncthreads();
 #pragma unroll
   for (int b = 0; b < 16; b++) sm[hi4 * 256 + lo4 + 16 * b] = v[af_dig(b)];
