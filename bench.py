@@ -14,8 +14,9 @@ steps).  Filter state carries from step to step exactly as in streaming use.
             CUDA events on the launch stream between barriers, max over ranks.
   e2e       the same K steps through the host-buffer C-ABI call pmr446_batch_execute(): pinned host IQ
             -> H2D -> chain -> D2H of the s16 audio, copies inside the timed region.
-  roofline  the dominant kernel (audio_kernel: 377-tap high-pass FIR + de-emphasis + s16), timed live with
-            CUDA events inside the timed steps; algorithmic FLOPs / measured FP32 FFMA peak.
+  roofline  the kernel with the longest launch, timed live with CUDA events inside the timed steps: algorithmic
+            bytes / measured HBM peak and algorithmic flop / measured FP32 FFMA peak, reported for the roofline that
+            binds (the larger fraction); "kernels" carries the same numbers for every launch of the step.
   cpu_baseline  the CPU oracle (port of the reference chain, all 16 channels) on all host cores.
 
 --impl reference times the reference's CPU chain (the oracle port -- the reference itself cannot be
@@ -43,7 +44,19 @@ UNIT = "Msamples/s"
 # algorithmic work of the 2.4 Msps / 16-channel chain
 FLOP_PER_SAMPLE = 122.1
 BYTES_PER_SAMPLE = 2.17
-AUDIO_FLOP_PER_OUT = 377 * 2 + 5   # HP FIR (2 flop per tap) + gain + de-emphasis, per 12.5 kHz channel sample
+# per kernel launch: algorithmic flop and HBM bytes per INPUT sample (SURVEY.md 8d table, 2.4 Msps column, divided
+# by 2.4e6; direct-form FIR counts; bytes = what the launch must read + write once), and what it replaces
+KERNELS = {
+    "cascade0": {"what": "cascade_kernel<cu8, DC, m=3, m=5>: cu8 load, DC blocker, two half-band decimators -> 600 kHz ring",
+                 "flop": (19.2 + 31.2 + 25.2) / 2.4, "bytes": 2.0 + 0.6e6 * 8 / 2.4e6},
+    "cascade1": {"what": "hbarb_tile_kernel<10, 2, 3>: m=10 half-band decimator + 14-tap arbitrary resampler -> 200 kHz ring",
+                 "flop": (24.6 + 11.2) / 2.4, "bytes": 0.6e6 * 8 / 2.4e6 + 0.2e6 * 8 / 2.4e6},
+    "channelize": {"what": "channelize16_kernel: NCO mix, 16 x 26-tap polyphase bank, 16-point DFT, FM discriminator",
+                   "flop": (1.2 + 20.8 + 4.0 + 3.8) / 2.4, "bytes": 0.2e6 * 8 / 2.4e6 + 0.2e6 * 4 / 2.4e6},
+    "audio": {"what": "audio_fft_kernel: 377-tap CTCSS high-pass FIR + gain + de-emphasis + s16 by 4096-point overlap-save "
+                      "(flop = direct-form count of SURVEY 8d; the kernel executes ~10x fewer)",
+              "flop": (150.8 + 1.0) / 2.4, "bytes": 0.2e6 * 4 / 2.4e6 + 0.2e6 * 2 / 2.4e6},
+}
 WORKLOAD = "configs[2]: %d independent 2.4 Msps cu8 PMR446 captures x 16 channels per GPU, 1 s of signal per step" % STREAMS
 
 
@@ -249,19 +262,41 @@ def run_ours(args, rank, world, local_rank):
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
-        a_ms, a_cnt = timings.get("audio", (0.0, 0))
-        a_avg = a_ms / max(a_cnt, 1)
-        a_flops = AUDIO_FLOP_PER_OUT * float(S) * 16 * 12500
-        a_tflops = a_flops / (a_avg * 1e-3) / 1e12 if a_avg > 0 else 0.0
         step_ms = ms_total / args.steps
         shares = {k: round(v[0] / max(v[1], 1) / step_ms, 4) for k, v in timings.items()}
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "audio_kernel_traffic.json")
+        hbm_peak = peaks.get("hbm_gbs")
+        traffic_all = {}
+        tpath = os.path.join(ROOT, "profiles", "kernel_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                traffic_all = json.load(f)
+        per_kernel = {}
+        for name, k in KERNELS.items():
+            ms, cnt = timings.get(name, (0.0, 0))
+            if not cnt:
+                continue
+            avg = ms / cnt                                  # one launch = one step's samples of this rank
+            tf = k["flop"] * float(S) * n / (avg * 1e-3) / 1e12
+            gbs = k["bytes"] * float(S) * n / (avg * 1e-3) / 1e9
+            per_kernel[name] = {"avg_launch_ms": avg, "share_of_step": shares.get(name), "tflops": tf, "fp32_frac": tf / fp32_peak,
+                                "gbs": gbs, "hbm_frac": gbs / hbm_peak}
+        dom = max(per_kernel, key=lambda q: per_kernel[q]["avg_launch_ms"])
+        dk = per_kernel[dom]
+        dom_hbm = dk["hbm_frac"] >= dk["fp32_frac"]
+        tr = traffic_all.get(dom)
+        roofline = {"kernel": dom + " -- " + KERNELS[dom]["what"], "bound": "hbm" if dom_hbm else "fp32",
+                    "achieved": dk["gbs"] if dom_hbm else dk["tflops"], "peak": hbm_peak if dom_hbm else fp32_peak,
+                    "unit": "GB/s" if dom_hbm else "TFLOP/s", "frac": dk["hbm_frac"] if dom_hbm else dk["fp32_frac"],
+                    "traffic": tr * (float(S) / 1024.0) if tr else None,
+                    "algorithmic_bytes_per_launch": KERNELS[dom]["bytes"] * float(S) * n,
+                    "algorithmic_flop_per_launch": KERNELS[dom]["flop"] * float(S) * n,
+                    "peak_source": (peak_src if dom_hbm else "FFMA issue peak measured live by pmr446_measure_fp32_peak "
+                                    "(MEASURED_PEAKS.json has no FP32 figure)"),
+                    "other_roofline_frac": dk["fp32_frac"] if dom_hbm else dk["hbm_frac"],
+                    "avg_launch_ms": dk["avg_launch_ms"], "share_of_step": dk["share_of_step"]}
         cores = os.cpu_count() or 1
-        cpu_v, cpu_dt = cpu_chain_rate(cores, 2)
+        cpu_v, cpu_dt = cpu_chain_rate(cores, 8)
+        cpu_f, cpu_fdt = cpu_chain_rate(cores, 8, active_only=1)   # what the reference executes: one demodulated channel
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -270,18 +305,18 @@ def run_ours(args, rank, world, local_rank):
                     "steps": e2e_steps, "api": "pmr446_batch_execute (host buffers, pinned)"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"kernel": "audio_kernel (377-tap CTCSS high-pass FIR + de-emphasis + s16)", "bound": "fp32", "achieved": a_tflops,
-                         "peak": fp32_peak, "unit": "TFLOP/s", "frac": a_tflops / fp32_peak if fp32_peak else None, "traffic": traffic,
-                         "peak_source": "FFMA issue peak measured live by pmr446_measure_fp32_peak (MEASURED_PEAKS.json has no FP32 figure)",
-                         "avg_launch_ms": a_avg, "share_of_step": shares.get("audio")},
+            "roofline": roofline,
+            "kernels": per_kernel,
             "chain_roofline": {"fp32": {"flop_per_sample": FLOP_PER_SAMPLE, "achieved_tflops": value * 1e6 * FLOP_PER_SAMPLE / 1e12 / world,
                                         "peak_tflops": fp32_peak, "frac": value * 1e6 * FLOP_PER_SAMPLE / 1e12 / world / fp32_peak},
                                "hbm": {"bytes_per_sample": BYTES_PER_SAMPLE, "achieved_gbs": value * 1e6 * BYTES_PER_SAMPLE / 1e9 / world,
-                                       "peak_gbs": peaks.get("hbm_gbs"), "frac": value * 1e6 * BYTES_PER_SAMPLE / 1e9 / world / peaks.get("hbm_gbs"),
+                                       "peak_gbs": hbm_peak, "frac": value * 1e6 * BYTES_PER_SAMPLE / 1e9 / world / hbm_peak,
                                        "peak_source": peak_src}},
             "kernel_share_of_step": shares,
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d host threads x 2 s of one 2.4 Msps stream each (all 16 channels demodulated), %.1f s wall" % (cores, cpu_dt)},
+                             "sample": "%d host threads x 8 s of one 2.4 Msps stream each (all 16 channels demodulated), %.1f s wall" % (cores, cpu_dt),
+                             "reference_faithful_value": cpu_f,
+                             "reference_faithful_sample": "same, only one channel demodulated as the reference does (SURVEY 8d), %.1f s wall" % cpu_fdt},
             "checksum": checksum,
             "per_rank": rank_stats,
         }
