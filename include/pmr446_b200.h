@@ -15,6 +15,10 @@
  *                                      :910-913 (asgram waterfall row).
  *   dsd446_batch_execute*()  replaces  src/dsd_in.c:167-175 (DC block, msresamp down, freqdem,
  *                                      msresamp_rrrf up, s16 conversion).
+ *   pmr446_receiver_execute*() replaces src/sdr_pmr446.c:795-913 as the reference runs it: the same
+ *                                      front half, then RSSI (:330-336, :668-700), the squelch /
+ *                                      selector state machine (:828-874), the selected channel's
+ *                                      audio chain (:876-908) and the CTCSS detector (:338-418, :605-628).
  *
  * The liquid-dsp-signature shim (second tier) is declared in pmr446_liquid_shim.h.
  * All arithmetic runs on the GPU; there is no CPU fallback: without a CUDA device every

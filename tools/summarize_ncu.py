@@ -80,11 +80,18 @@ def main():
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     with open(os.path.join(ROOT, "profiles", "ncu_%s_summary.md" % tag), "w") as f:
         f.write("\n".join(out))
-    aud = [v for k, v in traffic.items() if "audio_kernel" in k]
-    if aud:
-        with open(os.path.join(ROOT, "profiles", "audio_kernel_traffic.json"), "w") as f:
-            json.dump({"dram_bytes_per_launch": aud[0] * 1024 / streams, "measured_streams": streams, "scaled_to_streams": 1024,
-                       "source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, %s" % tag}, f)
+    # per-launch DRAM traffic keyed like bench.py's kernel table, scaled to 1024 streams
+    keymap = (("cascade_kernel<0", "cascade0"), ("hbarb_tile", "cascade1"), ("cascade_kernel<2", "cascade1"), ("channelize16", "channelize"),
+              ("audio_fft", "audio"), ("audio_kernel", "audio"))
+    kt = {}
+    for name, v in traffic.items():
+        for pat, key in keymap:
+            if pat in name and key not in kt:
+                kt[key] = v * 1024 / streams
+    if kt:
+        kt["_source"] = "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch at %d streams, scaled to 1024 (%s)" % (streams, tag)
+        with open(os.path.join(ROOT, "profiles", "kernel_traffic.json"), "w") as f:
+            json.dump(kt, f, indent=1)
     print("\n".join(out[-14:]))
 
 
