@@ -39,7 +39,7 @@ struct HbArbParams {
 };
 
 template <int M, int P, int Q>
-__global__ void __launch_bounds__(HT_THREADS, 5) hbarb_tile_kernel(HbArbParams p) {
+__global__ void __launch_bounds__(HT_THREADS, 6) hbarb_tile_kernel(HbArbParams p) {
   static_assert(P == 2 && HT_R % P == 0, "phase rows are passed for P = 2");
   constexpr int RH = HT_R / P * Q;          // half-band outputs per thread (12)
   constexpr int TH = RH * HT_THREADS;       // per tile
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(HT_THREADS, 5) hbarb_tile_kernel(HbArbParams p
   extern __shared__ float2 ht_smem[];
   float2* ev = ht_smem;                      // even-phase ring samples
   float2* od = ev + pad(NPAIR) + 1;          // odd-phase
-  float2* hbo = od + pad(NPAIR) + 1;         // half-band outputs
+  float2* hbo = ev;                          // half-band outputs overwrite the even-phase tile (after a barrier)
 
   const int t = threadIdx.x;
   const int s = blockIdx.x / p.tiles;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(HT_THREADS, 5) hbarb_tile_kernel(HbArbParams p
   // ---- half-band decimator (A.4): out[o] = odd[o - M] + sum_j h[j] even[o - j], times scale ---------------------
   {
     const int base = (RH + 1) * t;             // pad(RH t)
-    float2 e[RH + W];
+    float2 e[RH + W], hout[RH];
 #pragma unroll
     for (int c = 0; c < RH + W; c++) e[c] = ev[base + HT_HH + c + (HT_HH + c) / RH];
 #pragma unroll
@@ -144,8 +144,9 @@ __global__ void __launch_bounds__(HT_THREADS, 5) hbarb_tile_kernel(HbArbParams p
         ar = fmaf(p.hb[j], e[r + W - j].x, ar);
         ai = fmaf(p.hb[j], e[r + W - j].y, ai);
       }
-      hbo[base + (HT_HH + r) + (HT_HH + r) / RH] = make_float2(ar * p.scale, ai * p.scale);
+      hout[r] = make_float2(ar * p.scale, ai * p.scale);
     }
+    float2 hpre = make_float2(0.0f, 0.0f);
     if (t < HT_HH) {                           // the few outputs before the tile that the resampler window reaches
       const float2 o = od[pad(t + W - M)];
       float ar = o.x, ai = o.y;
@@ -155,8 +156,12 @@ __global__ void __launch_bounds__(HT_THREADS, 5) hbarb_tile_kernel(HbArbParams p
         ar = fmaf(p.hb[j], x.x, ar);
         ai = fmaf(p.hb[j], x.y, ai);
       }
-      hbo[pad(t)] = make_float2(ar * p.scale, ai * p.scale);
+      hpre = make_float2(ar * p.scale, ai * p.scale);
     }
+    __syncthreads();                           // everyone has read its even samples: the buffer is reused
+#pragma unroll
+    for (int r = 0; r < RH; r++) hbo[base + (HT_HH + r) + (HT_HH + r) / RH] = hout[r];
+    if (t < HT_HH) hbo[pad(t)] = hpre;
   }
   __syncthreads();
 
@@ -198,7 +203,8 @@ template <int M, int P, int Q>
 inline size_t hbarb_tile_smem() {
   constexpr int RH = HT_R / P * Q, TH = RH * HT_THREADS, W = 2 * M - 1, NPAIR = TH + HT_HH + W, NH = TH + HT_HH;
   auto pad = [](int i) { return i + i / RH; };
-  return (size_t)(2 * (pad(NPAIR) + 1) + pad(NH) + 1) * sizeof(float2);
+  (void)NH;
+  return (size_t)(2 * (pad(NPAIR) + 1)) * sizeof(float2);   // the half-band outputs reuse the even-phase buffer
 }
 
 }  // namespace pmr
