@@ -39,7 +39,7 @@ struct HbArbParams {
 };
 
 template <int M, int P, int Q>
-__global__ void __launch_bounds__(HT_THREADS, 6) hbarb_tile_kernel(HbArbParams p) {
+__global__ void __launch_bounds__(HT_THREADS, 7) hbarb_tile_kernel(HbArbParams p) {
   static_assert(P == 2 && HT_R % P == 0, "phase rows are passed for P = 2");
   constexpr int RH = HT_R / P * Q;          // half-band outputs per thread (12)
   constexpr int TH = RH * HT_THREADS;       // per tile
