@@ -60,6 +60,9 @@ KERNELS = {
 WORKLOAD = "configs[2]: %d independent 2.4 Msps cu8 PMR446 captures x 16 channels per GPU, 1 s of signal per step" % STREAMS
 
 
+emit = None   # set by main(): prints the one JSON line on the real stdout
+
+
 def config_dict(n_gpus):
     return {"workload": WORKLOAD, "streams_per_gpu": STREAMS, "fs_in": FS, "samples_per_stream_per_step": CHUNK,
             "channels": 16, "in_fmt": "cu8", "out": "s16 audio, 16 x 12.5 kHz per stream", "parallelism": "streams sharded, %d GPU(s)" % n_gpus,
@@ -150,7 +153,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    secs = 1
+    secs = 4
     vals = []
     for it in range(args.warmup + args.steps):
         v, dt = cpu_chain_rate(cores, secs)
@@ -165,7 +168,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference = CPU oracle port of the liquid-dsp chain (reference cannot be compiled here: liquid-dsp v1.7.0 absent)"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args, rank, world, local_rank):
@@ -320,7 +323,7 @@ def run_ours(args, rank, world, local_rank):
             "checksum": checksum,
             "per_rank": rank_stats,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     batch.close()
     if distributed:
         dist.destroy_process_group()
@@ -336,6 +339,17 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: anything libraries print meanwhile (NCCL's version banner, ...) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global emit
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:
