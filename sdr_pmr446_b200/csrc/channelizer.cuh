@@ -3,21 +3,25 @@
 // (nco_crcf_mix_down/step, firpfbch_crcf_analyzer_execute, transpose) and
 // freqdem_demodulate_block (:881) for every channel.
 //
-// One warp walks a tile of frames of one stream, two frames per step.  Lane l = (branch i = l & 15,
-// half h = l >> 4): the 26-tap branch filter is split in two 13-tap halves so that each lane keeps
-// only a 14-slot window in registers (rotation period 14 frames = 7 steps, the unrolled loop body).
-// Half 1 simply runs on the same sample stream delayed by 13 frames, so both halves execute the
-// same code.  The commutator sends resampled sample 16f + 15 - i to branch i; the NCO phasor of a
-// lane only depends on the frame parity when 32 dtheta = 0 mod 2^32 (the reference's 17/32-cycle
-// step), so mixing is one complex multiply by a per-lane constant.  Per step the halves swap one
-// partial sum (half 0 finishes the even frame, half 1 the odd one), each 16-lane half runs a
-// 4-stage decimation-in-frequency FFT with xor-shuffles (the lane holding DFT input n = 15 - i ends
-// with bin bitrev4(n), i.e. PMR channel c), and the discriminator arg(conj(y[f-1]) y[f]) runs with
-// the previous frame's value obtained from the other half.  A polynomial atan2 (|err| < 3e-7 rad)
-// replaces libm's.
+// One warp walks a tile of 140 frames of one stream in five batches of 28 frames.
+//  Phase A (two frames per step): lane l = (branch i = l & 15, half h = l >> 4); the 26-tap branch filter is split
+//   in two 13-tap halves so that each lane keeps only a 14-slot window in registers (rotation period 14 frames =
+//   7 steps, the unrolled loop body).  Half 1 runs on the same sample stream delayed by 13 frames, so both halves
+//   execute the same code.  The commutator sends resampled sample 16f + 15 - i to branch i; the NCO phasor of a lane
+//   only depends on the frame parity when 32 dtheta = 0 mod 2^32 (the reference's 17/32-cycle step), so mixing is one
+//   complex multiply by a per-lane constant.  The halves swap one partial sum per step and the finished dot product
+//   of frame k goes to shared memory, row k, column n = 15 - i (the DFT input index).
+//  Phase B: lane = frame: reads its 16 branch outputs (row stride 17: conflict-free), runs the forward 16-point DFT in
+//   registers (no shuffles) and writes channel-major rows [channel][1 + frame] (row stride 29).
+//  Phase C: lane = (channel, 14 consecutive frames): discriminator arg(conj(y[f-1]) y[f]) with a polynomial atan2
+//   (|err| < 3e-7 rad) and aligned two-sample stores into the channel's ring row; column 0 of each row carries the
+//   last frame of the previous batch.
+// The warp owns its shared-memory slice, so the phases are separated by __syncwarp() only.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include "audio_fft.cuh"   // dft16 / af_dig
 
 namespace pmr {
 
@@ -46,8 +50,9 @@ constexpr int CH_BODIES = 10;   // 10 bodies x 14 frames = 140 computed frames, 
 __device__ __forceinline__ float fast_atan2f(float y, float x) {
   const float ax = fabsf(x), ay = fabsf(y);
   const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-  if (mx == 0.0f) return atan2f(y, x);
-  const float a = __fdividef(mn, mx);
+  // (+-0, +-0): the quotient is taken as 0, and the quadrant comes from the SIGN BITS below, which gives libm's
+  // atan2(+-0, +0) = +-0 and atan2(+-0, -0) = +-pi without a branch
+  const float a = __fdividef(mn, mx == 0.0f ? 1.0f : mx);
   const float s = a * a;
   float r = 0.0028662257f;
   r = fmaf(r, s, -0.0161657367f);
@@ -60,15 +65,24 @@ __device__ __forceinline__ float fast_atan2f(float y, float x) {
   r = fmaf(r, s, 1.0f);
   r *= a;
   if (ay > ax) r = 1.57079632679489662f - r;
-  if (x < 0.0f) r = 3.14159265358979324f - r;
+  if (__float_as_int(x) < 0) r = 3.14159265358979324f - r;
   return copysignf(r, y);
 }
 
+constexpr int CH_BATCH = 28;               // frames per batch: two rotations of the 14-slot window
+constexpr int CH_NB = 5;                   // batches per tile (140 computed frames)
+constexpr int CH_A_STRIDE = 17;            // float2 per frame row of the branch-output buffer (16 + 1 pad)
+constexpr int CH_B_STRIDE = 29;            // float2 per channel row of the channel-output buffer (1 previous + 28)
+constexpr int CH_SMEM_WARP = CH_BATCH * CH_A_STRIDE + 16 * CH_B_STRIDE;
+
 template <bool NCO_CONST>
-__global__ void __launch_bounds__(128) channelize16_kernel(ChanParams p) {
+__global__ void __launch_bounds__(128, 5) channelize16_kernel(ChanParams p) {
+  __shared__ float2 ch_smem[4 * CH_SMEM_WARP];
   const int lane = threadIdx.x & 31, br = lane & 15, hsel = lane >> 4;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp >= (long long)p.n_streams * p.tiles) return;   // warp-uniform
+  float2* A = ch_smem + (threadIdx.x >> 5) * CH_SMEM_WARP;   // [frame of the batch][DFT input n]
+  float2* B = A + CH_BATCH * CH_A_STRIDE;                     // [channel][previous frame, 28 frames]
   const int s = (int)(warp / p.tiles);
   const long long tile = p.tile0 + (warp % p.tiles);
   const long long fa = tile * CH_TL, fs = fa - 4;          // computed frames are fs + k, k in [0, 140)
@@ -78,24 +92,9 @@ __global__ void __launch_bounds__(128) channelize16_kernel(ChanParams p) {
 #pragma unroll
   for (int n = 0; n < 13; n++) h[n] = __ldg(p.taps + br * 26 + 13 * hsel + n);
 
-  // FFT constants of this lane: DFT input index n = 15 - branch
-  const int nidx = 15 - br;
-  float sg[4], twr[3], twi[3];
-#pragma unroll
-  for (int st = 0; st < 4; st++) {
-    const int hh = 8 >> st;
-    const bool hi = (nidx & hh) != 0;
-    sg[st] = hi ? -1.0f : 1.0f;
-    if (st < 3) {
-      float sn = 0.0f, cs = 1.0f;
-      if (hi) sincospif(-(float)(nidx & (hh - 1)) / (float)hh, &sn, &cs);
-      twr[st] = cs;
-      twi[st] = sn;
-    }
-  }
-  const int c = ((nidx & 1) << 3) | ((nidx & 2) << 1) | ((nidx & 4) >> 1) | ((nidx & 8) >> 3);
-  float* drow = p.demod + ((long long)s * 16 + c) * p.demod_stride;
-  float2* crow = p.chan ? p.chan + ((long long)s * 16 + c) * p.chan_ld : nullptr;
+  // phase C of every batch: this lane owns channel br, frames 14 hsel .. 14 hsel + 13 of the batch
+  float* drow = p.demod + ((long long)s * 16 + br) * p.demod_stride;
+  float2* crow = p.chan ? p.chan + ((long long)s * 16 + br) * p.chan_ld : nullptr;
 
   // this lane's sample for (delayed) frame k: j = jb + 16 k; valid iff 0 <= j < r1
   const long long jb = 16 * (fs - 13 * hsel) + 15 - br;
@@ -144,70 +143,89 @@ __global__ void __launch_bounds__(128) channelize16_kernel(ChanParams p) {
   const int own_lo = (int)(lo64 < 0 ? 0 : (lo64 > 4096 ? 4096 : lo64)), own_hi = (int)(hi64 < 0 ? 0 : (hi64 > 4096 ? 4096 : hi64));
   const unsigned fs32 = (unsigned)fs, dmask = (unsigned)p.demod_mask;
   const int crel = (int)(fs - p.f0 < -(1ll << 30) ? -(1 << 30) : (fs - p.f0 > (1ll << 30) ? (1 << 30) : fs - p.f0));
-  // computed frame k of this lane is absolute frame 0 (stream start: r_prime = 0) when k == k_zero
-  const long long kz64 = -fs - hsel;
-  const int k_zero = (int)(kz64 < -1 ? -1 : (kz64 > 4096 ? -1 : kz64));
+  // computed frame k is absolute frame 0 (stream start: r_prime = 0) when k == k_zero
+  const int k_zero = (fs <= 0 && fs > -4096) ? (int)(-fs) : -1;
+  if (lane < 16) B[lane * CH_B_STRIDE] = make_float2(0.0f, 0.0f);   // "previous frame" of the first batch (never owned)
 
-  float sav_r = 0.0f, sav_i = 0.0f;   // half 0: y of the previous odd frame (from half 1)
   float2 n0 = fetch(0), n1 = fetch(1);
 #pragma unroll 1
-  for (int body = 0; body < CH_BODIES; body++) {
-    const int kb = 14 * body;
+  for (int batch = 0; batch < CH_NB; batch++) {
+    // ---- phase A: mix, branch filters; dot products of frame kk go to A[kk][15 - branch] ----------------------------
+#pragma unroll 1
+    for (int hb = 0; hb < 2; hb++) {
+      const int kb = CH_BATCH * batch + 14 * hb;
 #pragma unroll
-    for (int j = 0; j < 7; j++) {
-      const int k = kb + 2 * j;            // frames k (slot 2j) and k + 1 (slot 2j + 1)
-      mix(n0, k, 0, wr[2 * j], wi[2 * j]);
-      mix(n1, k + 1, 1, wr[2 * j + 1], wi[2 * j + 1]);
-      n0 = fetch(k + 2);                   // one step ahead
-      n1 = fetch(k + 3);
-      float d0r = 0.0f, d0i = 0.0f, d1r = 0.0f, d1i = 0.0f;
+      for (int j = 0; j < 7; j++) {
+        const int k = kb + 2 * j;            // frames k (slot 2j) and k + 1 (slot 2j + 1)
+        mix(n0, k, 0, wr[2 * j], wi[2 * j]);
+        mix(n1, k + 1, 1, wr[2 * j + 1], wi[2 * j + 1]);
+        n0 = fetch(k + 2);                   // one step ahead
+        n1 = fetch(k + 3);
+        float d0r = 0.0f, d0i = 0.0f, d1r = 0.0f, d1i = 0.0f;
 #pragma unroll
-      for (int n = 0; n < 13; n++) {
-        d0r = fmaf(h[n], wr[(2 * j - n + 14) % 14], d0r);
-        d0i = fmaf(h[n], wi[(2 * j - n + 14) % 14], d0i);
-        d1r = fmaf(h[n], wr[(2 * j + 1 - n + 14) % 14], d1r);
-        d1i = fmaf(h[n], wi[(2 * j + 1 - n + 14) % 14], d1i);
-      }
-      // half 0 completes frame k, half 1 frame k + 1: swap the other frame's partial sum
-      float ar = hsel ? d1r : d0r, ai = hsel ? d1i : d0i;
-      ar += __shfl_xor_sync(0xffffffffu, hsel ? d0r : d1r, 16);
-      ai += __shfl_xor_sync(0xffffffffu, hsel ? d0i : d1i, 16);
-      // 16-point DIF FFT within each half
-#pragma unroll
-      for (int st = 0; st < 4; st++) {
-        const int hh = 8 >> st;
-        const float br_ = __shfl_xor_sync(0xffffffffu, ar, hh);
-        const float bi_ = __shfl_xor_sync(0xffffffffu, ai, hh);
-        const float tr = fmaf(sg[st], ar, br_), ti = fmaf(sg[st], ai, bi_);
-        if (st < 3) {
-          ar = fmaf(tr, twr[st], -ti * twi[st]);
-          ai = fmaf(tr, twi[st], ti * twr[st]);
-        } else {
-          ar = tr; ai = ti;
+        for (int n = 0; n < 13; n++) {
+          d0r = fmaf(h[n], wr[(2 * j - n + 14) % 14], d0r);
+          d0i = fmaf(h[n], wi[(2 * j - n + 14) % 14], d0i);
+          d1r = fmaf(h[n], wr[(2 * j + 1 - n + 14) % 14], d1r);
+          d1i = fmaf(h[n], wi[(2 * j + 1 - n + 14) % 14], d1i);
         }
-      }
-      // discriminator (A.9): arg(conj(prev) * y) * ref with separate mul/add like the C reference
-      const float exr = __shfl_xor_sync(0xffffffffu, ar, 16), exi = __shfl_xor_sync(0xffffffffu, ai, 16);
-      float pr = hsel ? exr : sav_r, pi = hsel ? exi : sav_i;
-      sav_r = exr; sav_i = exi;
-      if (k == k_zero) { pr = 0.0f; pi = 0.0f; }
-      const float re = __fadd_rn(__fmul_rn(pr, ar), __fmul_rn(pi, ai));
-      const float im = __fsub_rn(__fmul_rn(pr, ai), __fmul_rn(pi, ar));
-      const float dm = fast_atan2f(im, re) * p.ref;
-      const float dm_o = __shfl_xor_sync(0xffffffffu, dm, 16);
-      // half 0 stores frames k, k + 1 (own value and the other half's); (fs + k) is even, so the pair
-      // is an aligned float2 unless the ownership boundary splits it
-      {
-        const bool a0 = (hsel == 0) && k >= own_lo && k < own_hi, a1 = (hsel == 0) && k + 1 >= own_lo && k + 1 < own_hi;
-        float* d = drow + ((fs32 + (unsigned)k) & dmask);
-        if (a0) d[0] = dm;
-        if (a1) d[1] = dm_o;
-        if (crow) {
-          if (a0) crow[crel + k] = make_float2(ar, ai);
-          if (a1) crow[crel + k + 1] = make_float2(exr, exi);
-        }
+        // half 0 completes frame k, half 1 frame k + 1: swap the other frame's partial sum
+        float ar = hsel ? d1r : d0r, ai = hsel ? d1i : d0i;
+        ar += __shfl_xor_sync(0xffffffffu, hsel ? d0r : d1r, 16);
+        ai += __shfl_xor_sync(0xffffffffu, hsel ? d0i : d1i, 16);
+        A[(14 * hb + 2 * j + hsel) * CH_A_STRIDE + 15 - br] = make_float2(ar, ai);
       }
     }
+    __syncwarp();
+    // ---- phase B: lane = frame of the batch: forward 16-point DFT in registers, transposed to B[channel][1 + frame] --
+    if (lane < CH_BATCH) {
+      float2 v[16];
+#pragma unroll
+      for (int n = 0; n < 16; n++) v[n] = A[lane * CH_A_STRIDE + n];
+      dft16<false>(v);
+#pragma unroll
+      for (int c = 0; c < 16; c++) B[c * CH_B_STRIDE + 1 + lane] = v[af_dig(c)];
+    }
+    __syncwarp();
+    // ---- phase C: lane = (channel br, frames 14 hsel ..): discriminator (A.9) arg(conj(prev) y) * ref with separate
+    // mul/add like the C reference, two-sample stores --------------------------------------------------------------------
+    {
+      const int k0 = CH_BATCH * batch + 14 * hsel;
+      const float2* brow = B + br * CH_B_STRIDE + 14 * hsel;
+      float2 prev = brow[0];
+      const bool all = k0 >= own_lo && k0 + 14 <= own_hi;
+      // (fs + k0) is even: a pair of frames is an aligned float2 of the ring and never straddles its end
+#pragma unroll 1
+      for (int i = 0; i < 14; i += 2) {
+        const float2 y0 = brow[1 + i], y1 = brow[2 + i];
+        if (k0 + i == k_zero) prev = make_float2(0.0f, 0.0f);
+        const float re0 = __fadd_rn(__fmul_rn(prev.x, y0.x), __fmul_rn(prev.y, y0.y));
+        const float im0 = __fsub_rn(__fmul_rn(prev.x, y0.y), __fmul_rn(prev.y, y0.x));
+        float2 p1 = y0;
+        if (k0 + i + 1 == k_zero) p1 = make_float2(0.0f, 0.0f);
+        const float re1 = __fadd_rn(__fmul_rn(p1.x, y1.x), __fmul_rn(p1.y, y1.y));
+        const float im1 = __fsub_rn(__fmul_rn(p1.x, y1.y), __fmul_rn(p1.y, y1.x));
+        const float2 dm = make_float2(fast_atan2f(im0, re0) * p.ref, fast_atan2f(im1, re1) * p.ref);
+        const int k = k0 + i;
+        float* d = drow + ((fs32 + (unsigned)k) & dmask);
+        if (all) {
+          *(float2*)d = dm;
+          if (crow) { crow[crel + k] = y0; crow[crel + k + 1] = y1; }
+        } else {
+          const bool a0 = k >= own_lo && k < own_hi, a1 = k + 1 >= own_lo && k + 1 < own_hi;
+          if (a0) d[0] = dm.x;
+          if (a1) d[1] = dm.y;
+          if (crow) {
+            if (a0) crow[crel + k] = y0;
+            if (a1) crow[crel + k + 1] = y1;
+          }
+        }
+        prev = y1;
+      }
+      __syncwarp();
+      if (hsel) B[br * CH_B_STRIDE] = prev;      // frame 27 of this batch is the next batch's previous frame
+    }
+    __syncwarp();
   }
 }
 
