@@ -177,3 +177,48 @@ def test_wideband_1600_channels_cf32():
             assert rel_rms(g["audio"][s, c, sl], r["audio"][c, sl]) < REL_RMS_TOL, ("audio", s, c)
             dp = np.abs(g["pcm"][s, c, sl].astype(np.int32) - r["pcm"][c, sl].astype(np.int32))
             assert dp.max() <= PCM_TOL_LSB, ("pcm", s, c, int(dp.max()))
+
+
+def test_2400k_awkward_chunks_exercise_tile_edges():
+    """2.4 Msps plan with chunk sizes that never align with the tiled kernels' grids (1024-output resampler tiles,
+    136-frame channelizer tiles, 3584-sample FFT audio tiles), including chunks shorter than one tile, odd sample
+    counts and empty calls.  Everything must equal the oracle's regular chunking."""
+    from oracle import oracle as orc
+    from sdr_pmr446_b200 import chain, synth
+    fs, n = 2400000, 700000
+    car = synth.rotated_carriers(5)
+    iq = synth.make_cu8(synth.CaptureSpec(fs=float(fs), carriers=car), n, 451)
+    gpu = chain.PmrBatch(n_streams=1, fs_in=fs, in_fmt=1, audio_gain=1.0, max_chunk=300000)
+    sizes = [1, 0, 7, 4097, 12289, 100001, 65537, 23, 300000, 199999, 18046]
+    assert sum(sizes) == n
+    parts, o = [], 0
+    for k in sizes:
+        parts.append(gpu.execute(iq[None, 2 * o:2 * (o + k)]))
+        o += k
+    gpu.close()
+    g = {"ny": sum(p["ny"] for p in parts), "ns": sum(p["ns"] for p in parts)}
+    for k in ("res", "chan", "demod", "lpcomp", "audio", "pcm"):
+        g[k] = np.concatenate([p[k] for p in parts], axis=-1)
+    ref = orc.PmrOracle(fs_in=fs, in_fmt=1, audio_gain=1.0, chunk=240000)
+    r = ref.run(iq, 240000)
+    ref.close()
+    _check(g, [r], [car])
+
+
+def test_2400k_cf32_lowpass_pcm_only():
+    """cf32 input at 2.4 Msps, audio low-pass on, only s16 requested (the benchmark's output set: FFT audio kernel alone)."""
+    from oracle import oracle as orc
+    from sdr_pmr446_b200 import chain, synth
+    fs, n = 2400000, 480000
+    car = synth.rotated_carriers(2)
+    iq = synth.make_cf32(synth.CaptureSpec(fs=float(fs), carriers=car), n, 452)
+    gpu = chain.PmrBatch(n_streams=1, fs_in=fs, in_fmt=0, audio_gain=2.0, lowpass=1, max_chunk=160000)
+    g = gpu.run(iq[None, :], 160000, want=("pcm",))
+    gpu.close()
+    ref = orc.PmrOracle(fs_in=fs, in_fmt=0, audio_gain=2.0, lowpass=1, chunk=160000)
+    r = ref.run(iq, 160000, want=("pcm", "demod"))
+    ref.close()
+    assert g["ns"] == r["ns"]
+    for c in active_channels(car):
+        dp = np.abs(g["pcm"][0, c, 600:].astype(np.int32) - r["pcm"][c, 600:].astype(np.int32))
+        assert dp.max() <= PCM_TOL_LSB, (c, int(dp.max()))
