@@ -240,7 +240,12 @@ struct Waterfall {
       double a = -2.0 * M_PI * (double)k / (double)nfft;
       tw[k] = make_float2((float)cos(a), (float)sin(a));
     }
-    parts = std::max(1, std::min(16, (296 + S - 1) / S));
+    // enough (stream, part) blocks to fill the GPU: one block needs nfft * 20 bytes of shared memory
+    {
+      const size_t per_block = (size_t)nfft * (2 * sizeof(float2) + sizeof(float));
+      const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / per_block));
+      parts = std::max(1, std::min(128, (148 * per_sm + S - 1) / S));
+    }
     int rc;
     if ((rc = d_window.alloc(W * sizeof(float))) || (rc = d_twiddle.alloc(nfft * sizeof(float2))) ||
         (rc = d_partial.alloc((size_t)S * parts * nfft * sizeof(float))) || (rc = d_scratch.alloc((size_t)S * nfft * sizeof(float))))
