@@ -222,3 +222,34 @@ def test_2400k_cf32_lowpass_pcm_only():
     for c in active_channels(car):
         dp = np.abs(g["pcm"][0, c, 600:].astype(np.int32) - r["pcm"][c, 600:].astype(np.int32))
         assert dp.max() <= PCM_TOL_LSB, (c, int(dp.max()))
+
+
+def test_five_channels_odd_row_count():
+    """A 5-channel plan (62.5 kHz from a 100 kHz cu8 capture: resampler rate 0.625, no half-band stage, prime-radix
+    DFT) with 3 streams: 15 channel rows, so the last FFT audio block has no partner row."""
+    from oracle import oracle as orc
+    from sdr_pmr446_b200 import chain, synth
+    M, fs, n, S = 5, 100000, 150000, 3
+    caps, cars = [], []
+    for s in range(S):
+        car = (synth.Carrier(1 + (s % M), 0.2, 1000.0, 67.0), synth.Carrier(1 + ((s + 2) % M), 0.1, 600.0, 88.5))
+        spec = synth.CaptureSpec(fs=float(fs), num_channels=M, carriers=car)
+        caps.append(synth.make_cu8(spec, n, 460 + s))
+        cars.append(car)
+    iq = np.stack(caps)
+    gpu = chain.PmrBatch(n_streams=S, fs_in=fs, in_fmt=1, num_channels=M, audio_gain=1.0, max_chunk=50000)
+    g = gpu.run(iq, 50000, want=("res", "chan", "demod", "audio", "pcm"))
+    gpu.close()
+    for s in range(S):
+        o = orc.PmrOracle(fs_in=fs, in_fmt=1, num_channels=M, audio_gain=1.0, chunk=50000)
+        r = o.run(iq[s], 50000)
+        o.close()
+        assert g["ny"] == r["ny"] and g["ns"] == r["ns"]
+        assert rel_rms(g["res"][s], r["res"]) < REL_RMS_TOL
+        assert rel_rms(g["chan"][s], r["chan"]) < REL_RMS_TOL
+        for c in active_channels(cars[s]):
+            sl = slice(1, None) if g["demod"][s, c, 0] == r["demod"][c, 0] else slice(500, None)
+            assert rel_rms(g["demod"][s, c, sl], r["demod"][c, sl]) < REL_RMS_TOL, ("demod", s, c)
+            assert rel_rms(g["audio"][s, c, sl], r["audio"][c, sl]) < REL_RMS_TOL, ("audio", s, c)
+            dp = np.abs(g["pcm"][s, c, sl].astype(np.int32) - r["pcm"][c, sl].astype(np.int32))
+            assert dp.max() <= PCM_TOL_LSB, ("pcm", s, c, int(dp.max()))
