@@ -99,7 +99,7 @@ __device__ __forceinline__ void wf_stage_generic(int R, const float2* __restrict
   }
 }
 
-static __global__ void __launch_bounds__(256) wf_accumulate_kernel(WfParams p) {
+static __global__ void __launch_bounds__(1024) wf_accumulate_kernel(WfParams p) {
   extern __shared__ float2 wf_smem[];
   float2* a = wf_smem;
   float2* b = wf_smem + p.nfft;
@@ -276,7 +276,8 @@ struct Waterfall {
     for (size_t i = 0; i < radix.size(); i++) p.radix[i] = radix[i];
     p.partial = (float*)d_partial.p;
     if (p.n_transforms > 0) {
-      wf_accumulate_kernel<<<S * parts, 256, smem, st>>>(p);
+      // a large transform leaves room for one block per SM only: give it 32 warps to hide the shared-memory latency
+      wf_accumulate_kernel<<<S * parts, smem > 48 * 1024 ? 1024 : 256, smem, st>>>(p);
       (*launches)++;
     }
     WfFinalParams f;
