@@ -171,12 +171,38 @@ def run_reference(args, rank, world):
     emit(line)
 
 
+def bind_near_gpu(local_rank):
+    """Pins this process to the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers of the
+    end-to-end arm are allocated next to the GPU's PCIe root (first-touch).  Returns the node or None."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from sdr_pmr446_b200 import chain
 
     torch.cuda.set_device(local_rank)
+    numa_node = bind_near_gpu(local_rank) if world > 1 else None
     dev = torch.device("cuda", local_rank)
     distributed = world > 1
     if distributed:
@@ -305,7 +331,8 @@ def run_ours(args, rank, world, local_rank):
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": S * n * 2, "d2h_bytes_per_step": S * 16 * int(e2e_ns) * 2,
-                    "steps": e2e_steps, "api": "pmr446_batch_execute (host buffers, pinned)"},
+                    "steps": e2e_steps, "api": "pmr446_batch_execute (host buffers, pinned)",
+                    "numa_bound": numa_node is not None},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roofline,
