@@ -326,6 +326,7 @@ def run_ours(args, rank, world, local_rank):
         cores = os.cpu_count() or 1
         cpu_v, cpu_dt = cpu_chain_rate(cores, 8)
         cpu_f, cpu_fdt = cpu_chain_rate(cores, 8, active_only=1)   # what the reference executes: one demodulated channel
+        cpu_1, _ = cpu_chain_rate(1, 8)                             # one stream on one core
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -345,6 +346,7 @@ def run_ours(args, rank, world, local_rank):
             "kernel_share_of_step": shares,
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d host threads x 8 s of one 2.4 Msps stream each (all 16 channels demodulated), %.1f s wall" % (cores, cpu_dt),
+                             "single_core_value": cpu_1,
                              "reference_faithful_value": cpu_f,
                              "reference_faithful_sample": "same, only one channel demodulated as the reference does (SURVEY 8d), %.1f s wall" % cpu_fdt},
             "checksum": checksum,
