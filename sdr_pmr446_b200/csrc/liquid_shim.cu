@@ -34,6 +34,54 @@ Scratch& scratch() {
 }
 bool have_device() { return select_device(-1) == 0; }
 
+// Small per-frame calls (nco_crcf_mix_block_down on 16 samples, firpfbch_crcf_analyzer_execute) are dominated by the
+// two synchronous copies around the kernel.  A page-locked, device-mapped staging pair lets the kernel read its input
+// and write its result over PCIe directly, and a completion word in the same kind of memory replaces the driver
+// synchronisation: one launch + a short spin per call.
+struct MappedPair {
+  void *in = nullptr, *out = nullptr;
+  size_t in_bytes = 0, out_bytes = 0;
+  ~MappedPair() {
+    if (in) cudaFreeHost(in);
+    if (out) cudaFreeHost(out);
+    if (flag) cudaFreeHost((void*)flag);
+  }
+  static int grow(void** p, size_t* have, size_t need) {
+    if (*p && *have >= need) return 0;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr;
+    size_t n = need < 4096 ? 4096 : need;
+    if (cudaHostAlloc(p, n, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); *p = nullptr; *have = 0; return -1; }
+    *have = n;
+    return 0;
+  }
+  volatile unsigned* flag = nullptr;   // completion word written by single-block kernels
+  unsigned seq = 0;
+  int ensure(size_t in_need, size_t out_need) {
+    if (!flag) {
+      void* f = nullptr;
+      if (cudaHostAlloc(&f, 64, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return -1; }
+      flag = (volatile unsigned*)f;
+      *flag = 0;
+    }
+    return grow(&in, &in_bytes, in_need) || grow(&out, &out_bytes, out_need);
+  }
+  // waits for the kernel launched with (flag, seq): spins on the mapped word for a bounded time, then falls back to
+  // a stream synchronisation (which also surfaces launch / execution errors)
+  int wait() {
+    if (cudaPeekAtLastError() == cudaSuccess) {
+      for (int spin = 0; spin < 200000; spin++)
+        if (*flag == seq) return 0;
+    }
+    return cudaStreamSynchronize(0) == cudaSuccess ? 0 : -1;
+  }
+};
+MappedPair& mapped() {
+  static thread_local MappedPair m;
+  return m;
+}
+constexpr size_t kMappedMax = 64 * 1024;   // larger blocks amortise the copies and use device staging
+
 // ---------------------------------------------------------------------------- first-order IIR
 // v[n] = x[n] + c v[n-1];  y[n] = b0 v[n] + b1 v[n-1]   (Direct Form II, A.1)
 constexpr int IIR_SEG = 256;
@@ -117,19 +165,30 @@ __global__ void freqdem_kernel(const float2* x /*[prev | x(n)]*/, int n, float r
 }
 
 // ---------------------------------------------------------------------------- NCO mix-down (A.7)
-__global__ void nco_mix_kernel(const float2* x, float2* y, int n, unsigned theta0, unsigned dtheta) {
+// `done` (optional, single-block launches only): a word in mapped host memory that receives `seq` once every result is
+// visible to the host, so the caller can wait on it instead of paying a driver synchronisation.
+__device__ __forceinline__ void signal_host(volatile unsigned* done, unsigned seq) {
+  __threadfence_system();
+  __syncthreads();
+  if (done && threadIdx.x == 0) *done = seq;
+}
+__global__ void nco_mix_kernel(const float2* x, float2* y, int n, unsigned theta0, unsigned dtheta, volatile unsigned* done = nullptr,
+                               unsigned seq = 0) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const unsigned th = theta0 + (unsigned)i * dtheta;
-  float sn, cs;
-  sincospif((float)(int)th * (1.0f / 2147483648.0f), &sn, &cs);
-  const float2 v = x[i];
-  y[i] = make_float2(fmaf(v.x, cs, v.y * sn), fmaf(v.y, cs, -v.x * sn));
+  if (i < n) {
+    const unsigned th = theta0 + (unsigned)i * dtheta;
+    float sn, cs;
+    sincospif((float)(int)th * (1.0f / 2147483648.0f), &sn, &cs);
+    const float2 v = x[i];
+    y[i] = make_float2(fmaf(v.x, cs, v.y * sn), fmaf(v.y, cs, -v.x * sn));
+  }
+  if (done) signal_host(done, seq);
 }
 
 // ---------------------------------------------------------------------------- analysis filter bank, one frame (A.8)
 // windows: [M][p] ring per branch (slot `pos` is the newest after the push).  Generic M (direct DFT).
-__global__ void pfbch_frame_kernel(const float2* x, float2* win, const float* taps, int M, int p, int pos, float2* y) {
+__global__ void pfbch_frame_kernel(const float2* x, float2* win, const float* taps, int M, int p, int pos, float2* y,
+                                   volatile unsigned* done = nullptr, unsigned seq = 0) {
   extern __shared__ float2 X[];
   for (int i = threadIdx.x; i < M; i += blockDim.x) {
     // commutator: x[k] goes to branch M-1-k  (filter_index starts at M-1 and decrements)
@@ -155,6 +214,7 @@ __global__ void pfbch_frame_kernel(const float2* x, float2* win, const float* ta
     }
     y[c] = make_float2(yr, yi);
   }
+  if (done) signal_host(done, seq);
 }
 
 }  // namespace
@@ -343,6 +403,20 @@ extern "C" int nco_crcf_step(nco_crcf q) {
   return LIQUID_OK;
 }
 static int nco_mix(nco_crcf q, const float2* x, float2* y, unsigned n, unsigned dtheta) {
+  if ((size_t)n * 8 <= kMappedMax) {
+    MappedPair& m = mapped();
+    if (m.ensure((size_t)n * 8, (size_t)n * 8)) return LIQUID_EICONFIG;
+    memcpy(m.in, x, (size_t)n * 8);
+    if (n <= 256) {
+      nco_mix_kernel<<<1, 256>>>((const float2*)m.in, (float2*)m.out, (int)n, q->theta, dtheta, m.flag, ++m.seq);
+      if (m.wait()) return LIQUID_EICONFIG;
+    } else {
+      nco_mix_kernel<<<(n + 255) / 256, 256>>>((const float2*)m.in, (float2*)m.out, (int)n, q->theta, dtheta);
+      CUDA_TRY(cudaStreamSynchronize(0));
+    }
+    memcpy(y, m.out, (size_t)n * 8);
+    return LIQUID_OK;
+  }
   Scratch& sc = scratch();
   if (sc.in.ensure((size_t)n * 8) || sc.out.ensure((size_t)n * 8)) return LIQUID_EICONFIG;
   CUDA_TRY(cudaMemcpy(sc.in.p, x, (size_t)n * 8, cudaMemcpyHostToDevice));
@@ -384,11 +458,22 @@ extern "C" firpfbch_crcf firpfbch_crcf_create_kaiser(int type, unsigned int M, u
 }
 extern "C" int firpfbch_crcf_analyzer_execute(firpfbch_crcf q, liquid_float_complex* x, liquid_float_complex* y) {
   if (!q || !x || !y) return LIQUID_EICONFIG;
-  CUDA_TRY(cudaMemcpy(q->x.p, x, (size_t)q->M * 8, cudaMemcpyHostToDevice));
+  const size_t bytes = (size_t)q->M * 8;
   q->pos = (q->pos + 1) % (int)q->p;
-  pfbch_frame_kernel<<<1, 256, (size_t)q->M * 8>>>((const float2*)q->x.p, (float2*)q->win.p, (const float*)q->taps.p, (int)q->M, (int)q->p, q->pos,
-                                                  (float2*)q->y.p);
-  CUDA_TRY(cudaMemcpy(y, q->y.p, (size_t)q->M * 8, cudaMemcpyDeviceToHost));
+  if (bytes <= kMappedMax) {
+    MappedPair& m = mapped();
+    if (m.ensure(bytes, bytes)) return LIQUID_EICONFIG;
+    memcpy(m.in, x, bytes);
+    pfbch_frame_kernel<<<1, 256, bytes>>>((const float2*)m.in, (float2*)q->win.p, (const float*)q->taps.p, (int)q->M, (int)q->p, q->pos,
+                                          (float2*)m.out, m.flag, ++m.seq);
+    if (m.wait()) return LIQUID_EICONFIG;
+    memcpy(y, m.out, bytes);
+    return LIQUID_OK;
+  }
+  CUDA_TRY(cudaMemcpy(q->x.p, x, bytes, cudaMemcpyHostToDevice));
+  pfbch_frame_kernel<<<1, 256, bytes>>>((const float2*)q->x.p, (float2*)q->win.p, (const float*)q->taps.p, (int)q->M, (int)q->p, q->pos,
+                                        (float2*)q->y.p);
+  CUDA_TRY(cudaMemcpy(y, q->y.p, bytes, cudaMemcpyDeviceToHost));
   return LIQUID_OK;
 }
 extern "C" int firpfbch_crcf_destroy(firpfbch_crcf q) { delete q; return LIQUID_OK; }
