@@ -10,6 +10,10 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box with -m gpu)")
+    # a fresh checkout has no built libraries: compile them once (nvcc cross-compiles sm_100a without a GPU)
+    from sdr_pmr446_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
 
 
 def _has_gpu():
