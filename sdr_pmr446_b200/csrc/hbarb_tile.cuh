@@ -3,13 +3,15 @@
 // P = 2 outputs per Q = 3 inputs).  Same arithmetic as cascade_kernel<SRC_RING, DC_NONE, 8, M, 0, 0, 0, true>
 // (/root/reference/src/sdr_pmr446.c:796 via liquid's msresamp2 + resamp), other mapping:
 //
-//   one block = one stream x one tile of 1024 resampler outputs (absolute grid, so chunk boundaries only move the
+//   one block = one stream x one tile of 768 resampler outputs (absolute grid, so chunk boundaries only move the
 //   ownership window [j0, j1)).  The 600 kHz ring samples of the tile (+ filter history) are staged in shared
 //   memory split in even / odd phases, with the zero-input-response correction of the DC blocker applied on the
-//   way in; every thread then computes 12 consecutive half-band outputs from a register window (31 even samples,
-//   20 taps as constant-bank operands: 504 FFMA per 43 LDS.64) into shared memory, and 8 consecutive resampler
-//   outputs from 24 of those (224 FFMA per 24 LDS.64); the two phase rows of the filter bank are kernel
-//   parameters.  One pad element every 12 makes the lane stride 13 (odd): conflict-free 64-bit accesses.
+//   way in; every thread then computes 9 consecutive half-band outputs from a register window (28 even samples,
+//   20 taps as constant-bank operands) into shared memory -- reusing the even-phase buffer -- and 6 consecutive
+//   resampler outputs from 21 of those; the two phase rows of the filter bank are kernel parameters.  With 6 outputs
+//   per thread the lane stride is 9 elements (odd): conflict-free 64-bit accesses without padding, 64 registers,
+//   19 KB of shared memory, 8 blocks per SM.  (8 outputs per thread needed one pad per 12 elements, whose jumps cost
+//   a bank conflict on every staging store: 1.44 vs 1.39 ms; 10 per thread: 126 registers, 1.49 ms.)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -19,7 +21,7 @@
 namespace pmr {
 
 constexpr int HT_THREADS = 128;
-constexpr int HT_R = 8;                    // resampler outputs per thread
+constexpr int HT_R = 6;                  // resampler outputs per thread
 constexpr int HT_TJ = HT_THREADS * HT_R;   // resampler outputs per tile
 constexpr int HT_HH = 16;                  // half-band outputs recomputed before the tile (>= 13 taps of history)
 
@@ -39,14 +41,15 @@ struct HbArbParams {
 };
 
 template <int M, int P, int Q>
-__global__ void __launch_bounds__(HT_THREADS, 7) hbarb_tile_kernel(HbArbParams p) {
+__global__ void __launch_bounds__(HT_THREADS, 8) hbarb_tile_kernel(HbArbParams p) {
   static_assert(P == 2 && HT_R % P == 0, "phase rows are passed for P = 2");
   constexpr int RH = HT_R / P * Q;          // half-band outputs per thread (12)
   constexpr int TH = RH * HT_THREADS;       // per tile
   constexpr int W = 2 * M - 1;              // previous even samples a half-band output needs
   constexpr int NPAIR = TH + HT_HH + W;     // (even, odd) pairs staged per tile
-  static_assert(RH % 2 == 0, "lane stride RH + 1 must be odd");
-  auto pad = [](int i) { return i + i / RH; };
+  // lane stride in float2 units must be odd for conflict-free 64-bit accesses: RH itself when odd, else one pad per RH
+  constexpr int PADK = (RH % 2 == 0) ? 1 : 0;
+  auto pad = [](int i) { return i + PADK * (i / RH); };
   extern __shared__ float2 ht_smem[];
   float2* ev = ht_smem;                      // even-phase ring samples
   float2* od = ev + pad(NPAIR) + 1;          // odd-phase
@@ -131,13 +134,13 @@ __global__ void __launch_bounds__(HT_THREADS, 7) hbarb_tile_kernel(HbArbParams p
 
   // ---- half-band decimator (A.4): out[o] = odd[o - M] + sum_j h[j] even[o - j], times scale ---------------------
   {
-    const int base = (RH + 1) * t;             // pad(RH t)
+    const int base = (RH + PADK) * t;             // pad(RH t)
     float2 e[RH + W], hout[RH];
 #pragma unroll
-    for (int c = 0; c < RH + W; c++) e[c] = ev[base + HT_HH + c + (HT_HH + c) / RH];
+    for (int c = 0; c < RH + W; c++) e[c] = ev[base + HT_HH + c + PADK * ((HT_HH + c) / RH)];
 #pragma unroll
     for (int r = 0; r < RH; r++) {
-      const float2 o = od[base + (HT_HH + W - M + r) + (HT_HH + W - M + r) / RH];
+      const float2 o = od[base + (HT_HH + W - M + r) + PADK * ((HT_HH + W - M + r) / RH)];
       float ar = o.x, ai = o.y;
 #pragma unroll
       for (int j = 0; j < 2 * M; j++) {
@@ -160,18 +163,18 @@ __global__ void __launch_bounds__(HT_THREADS, 7) hbarb_tile_kernel(HbArbParams p
     }
     __syncthreads();                           // everyone has read its even samples: the buffer is reused
 #pragma unroll
-    for (int r = 0; r < RH; r++) hbo[base + (HT_HH + r) + (HT_HH + r) / RH] = hout[r];
+    for (int r = 0; r < RH; r++) hbo[base + (HT_HH + r) + PADK * ((HT_HH + r) / RH)] = hout[r];
     if (t < HT_HH) hbo[pad(t)] = hpre;
   }
   __syncthreads();
 
   // ---- arbitrary resampler (A.5): output j sits at input floor(j step / 2^24) with bank row (j mod P) -----------
   {
-    const int base = (RH + 1) * t;
+    const int base = (RH + PADK) * t;
     constexpr int NW = RH + 12;                // inputs 12 t + HH - 13 .. 12 t + HH + RH - 2
     float2 w[NW];
 #pragma unroll
-    for (int c = 0; c < NW; c++) w[c] = hbo[base + (HT_HH - 13 + c) + (HT_HH - 13 + c) / RH];
+    for (int c = 0; c < NW; c++) w[c] = hbo[base + (HT_HH - 13 + c) + PADK * ((HT_HH - 13 + c) / RH)];
     float out[2 * HT_R];
 #pragma unroll
     for (int r = 0; r < HT_R; r++) {
@@ -188,9 +191,10 @@ __global__ void __launch_bounds__(HT_THREADS, 7) hbarb_tile_kernel(HbArbParams p
     const long long j = jt + HT_R * t;
     float2* dst = p.dst + (long long)s * p.dst_stride;
     if (j >= p.j0 && j + HT_R <= p.j1) {
-      float2* d = dst + (j & p.dst_mask);      // j is a multiple of 8: 64-byte aligned, never wraps inside
-      stg256(d, out);
-      stg256(d + 4, out + 8);
+      // j is even: 16-byte pieces are aligned and never straddle the ring's end
+#pragma unroll
+      for (int r = 0; r < HT_R; r += 2)
+        *(float4*)(dst + ((j + r) & p.dst_mask)) = make_float4(out[2 * r], out[2 * r + 1], out[2 * r + 2], out[2 * r + 3]);
     } else {
 #pragma unroll
       for (int r = 0; r < HT_R; r++)
@@ -202,7 +206,7 @@ __global__ void __launch_bounds__(HT_THREADS, 7) hbarb_tile_kernel(HbArbParams p
 template <int M, int P, int Q>
 inline size_t hbarb_tile_smem() {
   constexpr int RH = HT_R / P * Q, TH = RH * HT_THREADS, W = 2 * M - 1, NPAIR = TH + HT_HH + W, NH = TH + HT_HH;
-  auto pad = [](int i) { return i + i / RH; };
+  auto pad = [](int i) { return i + ((RH % 2 == 0) ? i / RH : 0); };
   (void)NH;
   return (size_t)(2 * (pad(NPAIR) + 1)) * sizeof(float2);   // the half-band outputs reuse the even-phase buffer
 }
