@@ -457,6 +457,16 @@ __global__ void __launch_bounds__(128, 3) cascade_kernel(CascadeParams p) {
   constexpr int NST = (MA > 0) + (MB > 0) + (MC > 0) + (MD > 0);
   constexpr int D = 1 << NST;
   constexpr int NO = G / D;  // outputs per iteration
+  // The lanes of a warp sit at different resampler phases unless the plan is periodic, so every output reads a
+  // different row of the filter bank: from global memory that is one L1 wavefront per lane and load.  A copy in
+  // shared memory with rows 20 floats apart (16-byte aligned, 8 bank groups) serves a quarter-warp per wavefront.
+  constexpr int BANK_STRIDE = 20;
+  __shared__ __align__(16) float sbank[ARB ? 256 * BANK_STRIDE : 4];
+  if (ARB) {
+    const int rows = 1 << p.bits;   // <= 256 (checked by the host)
+    for (int i = threadIdx.x; i < rows * 16; i += blockDim.x) sbank[(i >> 4) * BANK_STRIDE + (i & 15)] = __ldg(p.pfb + i);
+    __syncthreads();
+  }
   long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= (long long)p.n_streams * p.nseg) return;
   const int s = (int)(gid / p.nseg), t = (int)(gid % p.nseg);
@@ -577,8 +587,8 @@ __global__ void __launch_bounds__(128, 3) cascade_kernel(CascadeParams p) {
           if (all || (b >= lo && b < hi)) {
             // decimating plans have step >= 2^24: at most one output per pushed sample
             if (phase < (1u << 24)) {
-              const float4* row = (const float4*)(p.pfb + ((phase >> (24 - p.bits)) << 4));
-              const float4 h0 = __ldg(row), h1 = __ldg(row + 1), h2 = __ldg(row + 2), h3 = __ldg(row + 3);
+              const float4* row = (const float4*)(sbank + (phase >> (24 - p.bits)) * BANK_STRIDE);
+              const float4 h0 = row[0], h1 = row[1], h2 = row[2], h3 = row[3];
               const float h[14] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w, h2.x, h2.y, h2.z, h2.w, h3.x, h3.y};
               float yr = 0.0f, yi = 0.0f;
 #pragma unroll

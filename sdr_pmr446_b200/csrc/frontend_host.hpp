@@ -136,6 +136,7 @@ struct Frontend {
     plan = design::msresamp_plan(rate, as);
     if (plan.sub_len != 14) return fail(PMR446_EINVAL, "arbitrary resampler kernel is specialised for 14 taps");
     if (plan.step < (1u << 24)) return fail(PMR446_EINVAL, "internal: decimating plan with arbitrary rate > 1");
+    if (plan.bits > 8) return fail(PMR446_EINVAL, "resampler filter bank larger than 256 rows");
     // execution-order stage list: plan.m[stages-1] runs first
     std::vector<int> order;
     for (int g = (int)plan.stages - 1; g >= 0; g--) order.push_back((int)plan.m[g]);
