@@ -39,7 +39,7 @@ struct ChanGenParams {
   long long tile0;
   long long f0, f1;        // owned frames
   float ref;
-  const float* taps;       // [M][p] newest first
+  const float* taps;       // [p][M]: tap n (newest first) of every branch, contiguous over the branches
   const float2* twiddle;   // [M]
   int n_stages;
   int radix[16];
@@ -70,12 +70,12 @@ static __global__ void __launch_bounds__(256) channelize_generic_kernel(ChanGenP
     for (int i = threadIdx.x; i < M; i += blockDim.x) {
       // commutator: sample M f + (M - 1 - i) goes to branch i; X[M - 1 - i] = dot(branch i)
       float ar = 0.0f, ai = 0.0f;
-      const float* h = p.taps + (size_t)i * p.p;
+      const float* h = p.taps + i;
       for (int n = 0; n < p.p; n++) {
         const long long j = (long long)M * (f - n) + (M - 1 - i);
         if (j >= 0 && j < p.r1) {
           const float2 v = x[j & p.mask];
-          const float t = __ldg(h + n);
+          const float t = __ldg(h + (size_t)n * M);
           ar = fmaf(t, v.x, ar);
           ai = fmaf(t, v.y, ai);
         }

@@ -122,6 +122,14 @@ extern "C" int pmr446_batch_create(const pmr446_config* cfg, pmr446_batch** out)
   // channelizer (A.7, A.8)
   std::vector<float> taps = design::pfbch_taps((unsigned)M, cfg->pfb_m, cfg->pfb_as);
   if ((rc = b->d_pfb_taps.alloc(taps.size() * sizeof(float)))) { pmr446_batch_destroy(b); return rc; }
+  if (b->generic) {
+    // the generic kernel walks the branches across lanes: store tap n of all branches contiguously ([n][M])
+    const unsigned pp = 2 * cfg->pfb_m;
+    std::vector<float> tt(taps.size());
+    for (unsigned i = 0; i < (unsigned)M; i++)
+      for (unsigned n = 0; n < pp; n++) tt[(size_t)n * M + i] = taps[(size_t)i * pp + n];
+    taps.swap(tt);
+  }
   cudaMemcpy(b->d_pfb_taps.p, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice);
   float offset = -0.5f * (float)(cfg->num_channels - 1) / (float)cfg->num_channels * 2 * M_PI;  // :432-433
   b->dtheta = design::nco_dtheta(offset);
