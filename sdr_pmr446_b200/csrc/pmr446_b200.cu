@@ -55,7 +55,8 @@ struct pmr446_batch {
   // staging for the host-buffer call
   DevBuf d_in2[2], d_out_res, d_out_chan, d_out_demod, d_out_lpcomp, d_out_audio, d_out_pcm, d_out_ascii, d_out_peak, d_out_psd;
   long long max_res = 0, max_ns = 0;
-  cudaStream_t own_stream = nullptr, copy_stream = nullptr;
+  cudaStream_t own_stream = nullptr, copy_stream = nullptr, out_stream = nullptr;
+  cudaEvent_t ev_out = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   int launches = 0;
   Timer timer;
@@ -225,6 +226,8 @@ extern "C" int pmr446_batch_create(const pmr446_config* cfg, pmr446_batch** out)
   cudaFuncSetAttribute(audio_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   CUDA_TRY(cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&b->out_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&b->ev_out, cudaEventDisableTiming));
   for (int i = 0; i < 2; i++) {
     CUDA_TRY(cudaEventCreateWithFlags(&b->ev_copied[i], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&b->ev_free[i], cudaEventDisableTiming));
@@ -240,6 +243,8 @@ extern "C" int pmr446_batch_destroy(pmr446_batch* b) {
   cudaDeviceSynchronize();
   if (b->own_stream) cudaStreamDestroy(b->own_stream);
   if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
+  if (b->out_stream) cudaStreamDestroy(b->out_stream);
+  if (b->ev_out) cudaEventDestroy(b->ev_out);
   for (int i = 0; i < 2; i++) {
     if (b->ev_copied[i]) cudaEventDestroy(b->ev_copied[i]);
     if (b->ev_free[i]) cudaEventDestroy(b->ev_free[i]);
@@ -486,6 +491,22 @@ extern "C" int pmr446_batch_execute(pmr446_batch* b, const void* iq, long long i
   unsigned ny_tot = 0, ns_tot = 0;
   int launches = 0;
   unsigned off = 0;
+  // device -> host copies of a column range of every requested output; with time slices they run on their own stream
+  // right behind each slice's kernels, i.e. concurrently with the next slices' host -> device copies (PCIe is duplex)
+  auto back = [&](cudaStream_t s2, void* host, const void* dev, long long hld, long long dld, size_t elt, long long rows, long long col0,
+                  long long cols) {
+    if (host && cols > 0)
+      cudaMemcpy2DAsync((char*)host + col0 * elt, hld * elt, (const char*)dev + col0 * elt, dld * elt, cols * elt, rows, cudaMemcpyDeviceToHost, s2);
+  };
+  auto back_range = [&](cudaStream_t s2, unsigned y0, unsigned ny_k, unsigned s0, unsigned ns_k) {
+    back(s2, out->res, d.res, out->res_ld, rld, 8, S, y0, ny_k);
+    back(s2, out->chan, d.chan, out->ld, ld, 8, (long long)S * M, s0, ns_k);
+    back(s2, out->demod, d.demod, out->ld, ld, 4, (long long)S * M, s0, ns_k);
+    back(s2, out->lpcomp, d.lpcomp, out->ld, ld, 4, (long long)S * M, s0, ns_k);
+    back(s2, out->audio, d.audio, out->ld, ld, 4, (long long)S * M, s0, ns_k);
+    back(s2, out->pcm, d.pcm, out->ld, ld, 2, (long long)S * M, s0, ns_k);
+  };
+  const bool any_rows = out->chan || out->demod || out->lpcomp || out->audio || out->pcm;
   for (unsigned k = 0; k == 0 || off < n; k++) {
     const unsigned len = std::min(sub, n - off);
     const int buf = (int)(k & 1u);
@@ -506,29 +527,30 @@ extern "C" int pmr446_batch_execute(pmr446_batch* b, const void* iq, long long i
     if (rc) return rc;
     launches += b->launches;
     CUDA_TRY(cudaEventRecord(b->ev_free[buf], st));
+    if ((out->res && ny_tot + ny > out->res_ld) || (any_rows && ns_tot + ns > out->ld)) {
+      cudaStreamSynchronize(st);
+      cudaStreamSynchronize(b->out_stream);
+      return fail(PMR446_ERANGE, out->res && ny_tot + ny > out->res_ld ? "res_ld too small" : "ld too small");
+    }
+    if (K > 1) {
+      CUDA_TRY(cudaEventRecord(b->ev_out, st));
+      CUDA_TRY(cudaStreamWaitEvent(b->out_stream, b->ev_out, 0));
+      back_range(b->out_stream, ny_tot, ny, ns_tot, ns);
+    }
     ny_tot += ny;
     ns_tot += ns;
     off += len;
   }
   b->launches = launches;
   const unsigned ny = ny_tot, ns = ns_tot;
-  if (out->res && ny > out->res_ld) return fail(PMR446_ERANGE, "res_ld too small");
-  if ((out->chan || out->demod || out->lpcomp || out->audio || out->pcm) && ns > out->ld) return fail(PMR446_ERANGE, "ld too small");
-  auto back = [&](void* host, const void* dev, long long hld, long long dld, size_t elt, long long rows, long long cols) {
-    if (host && cols > 0) cudaMemcpy2DAsync(host, hld * elt, dev, dld * elt, cols * elt, rows, cudaMemcpyDeviceToHost, st);
-  };
-  back(out->res, d.res, out->res_ld, rld, 8, S, ny);
-  back(out->chan, d.chan, out->ld, ld, 8, (long long)S * M, ns);
-  back(out->demod, d.demod, out->ld, ld, 4, (long long)S * M, ns);
-  back(out->lpcomp, d.lpcomp, out->ld, ld, 4, (long long)S * M, ns);
-  back(out->audio, d.audio, out->ld, ld, 4, (long long)S * M, ns);
-  back(out->pcm, d.pcm, out->ld, ld, 2, (long long)S * M, ns);
+  if (K == 1) back_range(st, 0, ny, 0, ns);
   if (W) {
-    back(out->ascii, d.ascii, W, W, 1, S, W);
-    back(out->peak, d.peak, 2, 2, 4, S, 2);
-    back(out->psd, d.psd, 4 * W, 4 * W, 4, S, 4 * W);
+    back(st, out->ascii, d.ascii, W, W, 1, S, 0, W);
+    back(st, out->peak, d.peak, 2, 2, 4, S, 0, 2);
+    back(st, out->psd, d.psd, 4 * W, 4 * W, 4, S, 0, 4 * W);
   }
   CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaStreamSynchronize(b->out_stream));
   if (ny_out) *ny_out = ny;
   if (ns_out) *ns_out = ns;
   return PMR446_OK;
