@@ -10,8 +10,8 @@
 // of the direct form.
 //
 // FFT layout: 256 threads x 16 points in registers, three radix-16 passes (4096 = 16^3), data exchanged through
-// shared memory between passes (conflict-free: 16-lane groups read consecutive or stride-17 elements), twiddles from
-// a 4096-entry table.  The forward transform leaves X[k2 + 16 k1 + 256 k0] in register k0 of thread 16 k2 + k1; H is
+// shared memory between passes (conflict-free: 16-lane groups read consecutive or stride-17 elements); the inter-pass
+// twiddles are powers of one table entry per thread and pass, built by a depth-4 product tree in registers.  The forward transform leaves X[k2 + 16 k1 + 256 k0] in register k0 of thread 16 k2 + k1; H is
 // stored in that order and the inverse transform walks the same exchanges backwards, so no reordering pass exists.
 #pragma once
 #include <cuda_runtime.h>
