@@ -16,22 +16,22 @@ pytestmark = pytest.mark.gpu
 EXACT = ("state", "active_chan", "n_audio", "tone_detected", "ctcss_index", "events")
 
 
-def _pair(carrier_sets, chunk=sc.CHUNK, **kw):
+def _pair(carrier_sets, chunk=sc.CHUNK, fs=sc.FS, **kw):
     from oracle import oracle as orc
     from sdr_pmr446_b200 import chain
-    iq = np.stack([sc.capture(c, 446 + s) for s, c in enumerate(carrier_sets)])
-    rx = chain.PmrReceiver(n_streams=len(carrier_sets), fs_in=sc.FS, in_fmt=1, max_chunk=chunk, audio_gain=1.0, **kw)
+    iq = np.stack([sc.capture(c, 446 + s, fs=fs) for s, c in enumerate(carrier_sets)])
+    rx = chain.PmrReceiver(n_streams=len(carrier_sets), fs_in=fs, in_fmt=1, max_chunk=chunk, audio_gain=1.0, **kw)
     g = rx.run(iq, chunk)
     rx.close()
     refs = []
     for s in range(len(carrier_sets)):
-        o = orc.RxOracle(fs_in=sc.FS, in_fmt=1, chunk=chunk, audio_gain=1.0, **kw)
+        o = orc.RxOracle(fs_in=fs, in_fmt=1, chunk=chunk, audio_gain=1.0, **kw)
         refs.append(o.run(iq[s], chunk))
         o.close()
     return g, refs
 
 
-def _check(g, refs, carrier_sets, chunk=sc.CHUNK):
+def _check(g, refs, carrier_sets, chunk=sc.CHUNK, fs=sc.FS):
     for s, (rows, car) in enumerate(zip(refs, carrier_sets)):
         assert len(g) == len(rows)
         for k, (a, r) in enumerate(zip(g, rows)):
@@ -44,7 +44,7 @@ def _check(g, refs, carrier_sets, chunk=sc.CHUNK):
             scale = max(float(np.max(r["ctcss_power"])), 1.0)
             assert np.max(np.abs(a["ctcss_power"][s] - r["ctcss_power"])) / scale < 1e-3, ("ctcss_power", s, k)
             assert abs(float(a["max_power"][s]) - r["max_power"]) / scale < 1e-3, ("max_power", s, k)
-        good = sc.steady_chunks(rows, car, chunk)
+        good = sc.steady_chunks(rows, car, chunk, fs)
         assert len(good) >= 8, good
         ga = np.concatenate([g[k]["audio"][s, :rows[k]["n_audio"]] for k in good])
         ra = np.concatenate([rows[k]["audio"] for k in good])
@@ -107,3 +107,11 @@ def test_uneven_chunks_and_reset():
             assert int(a[f][0]) == int(b[f][0]) == int(r[f]), f
         assert np.array_equal(a["audio"][0, :r["n_audio"]], b["audio"][0, :r["n_audio"]])
         assert np.array_equal(a["rssi_ch"], b["rssi_ch"])
+
+
+def test_receiver_on_2400k_captures():
+    """The same scenarios from 2.4 Msps captures (tiled front-end kernels, 240 000-sample chunks = 1250 frames)."""
+    sets = (sc.keyed_two_calls(), sc.stronger_later())
+    g, refs = _pair(sets, chunk=240000, fs=2400000, lock_mode=1)
+    _check(g, refs, sets, chunk=240000, fs=2400000)
+    assert int(g[-1]["active_chan"][0]) == 6 and int(g[-1]["active_chan"][1]) == 14
