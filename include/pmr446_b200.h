@@ -81,6 +81,11 @@ typedef struct {
   char *ascii;             /* [n_streams][W] waterfall row (asgramcf_execute, :912) */
   float *peak;             /* [n_streams][2] peak value (dB) and frequency */
   float *psd;              /* [n_streams][4W] dB values behind the row */
+  /* Selector taps, 16-channel kernel only, one call = one RSSI window (average_power, :330-336; find_max_rssi_channel
+   * reads them, :668-700).  With the host-buffer call they switch the time slicing off. */
+  float *rssi;             /* [n_streams][M] 20 log10(mean |chan|) over this call's ns frames, dB */
+  float *chan_edge;        /* [n_streams][M][2] complex: channel sample of this call's first and last frame
+                              (what freqdem's r_prime needs when the active channel changes, :866, :881) */
 } pmr446_outputs;
 
 typedef struct pmr446_batch pmr446_batch;
@@ -101,6 +106,10 @@ int pmr446_batch_execute(pmr446_batch *b, const void *iq, long long iq_stride, u
  * `cuda_stream` (a cudaStream_t, NULL = default stream) and the call returns without waiting. */
 int pmr446_batch_execute_device(pmr446_batch *b, const void *iq, long long iq_stride, unsigned n, const pmr446_outputs *out,
                                 unsigned *ny, unsigned *ns, void *cuda_stream);
+/* Device call: demod_out[s][k] = discriminator output of channel `channel[s]` (device array, -1 = skip the stream) for the
+ * ns frames of the LAST execute call, read from the library's discriminator ring -- the squelch selector's tap
+ * (src/sdr_pmr446.c:876-881) without materialising all M rows. */
+int pmr446_batch_gather_channel(pmr446_batch *b, const int *channel, float *demod_out, long long ld, void *cuda_stream);
 /* Kernels launched by the last execute call (for the benchmark's gpu_launches field). */
 int pmr446_batch_last_launches(const pmr446_batch *b);
 /* Resets all filter state to stream start (t = 0). */

@@ -29,7 +29,7 @@ class Outputs(C.Structure):
     """pmr446_outputs (include/pmr446_b200.h)."""
     _fields_ = [("res", C.c_void_p), ("res_ld", C.c_longlong), ("chan", C.c_void_p), ("demod", C.c_void_p),
                 ("lpcomp", C.c_void_p), ("audio", C.c_void_p), ("pcm", C.c_void_p), ("ld", C.c_longlong),
-                ("ascii", C.c_void_p), ("peak", C.c_void_p), ("psd", C.c_void_p)]
+                ("ascii", C.c_void_p), ("peak", C.c_void_p), ("psd", C.c_void_p), ("rssi", C.c_void_p), ("chan_edge", C.c_void_p)]
 
 
 class RxConfig(C.Structure):
@@ -67,6 +67,7 @@ class DsdOutputs(C.Structure):
 EXPORTS = [
     "pmr446_default_config", "pmr446_batch_create", "pmr446_batch_destroy", "pmr446_batch_max_res",
     "pmr446_batch_max_ns", "pmr446_batch_execute", "pmr446_batch_execute_device", "pmr446_batch_last_launches",
+    "pmr446_batch_gather_channel",
     "pmr446_batch_reset", "pmr446_last_error", "pmr446_host_alloc", "pmr446_host_free", "pmr446_measure_fp32_peak", "pmr446_batch_timing",
     "pmr446_batch_get_timings",
     "pmr446_rx_default_config", "pmr446_receiver_create", "pmr446_receiver_destroy", "pmr446_receiver_max_ns",
@@ -107,6 +108,7 @@ def lib():
         L.pmr446_batch_execute_device.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_uint, C.POINTER(Outputs),
                                                   C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.c_void_p]
         L.pmr446_batch_last_launches.argtypes = [C.c_void_p]
+        L.pmr446_batch_gather_channel.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
         L.pmr446_batch_reset.argtypes = [C.c_void_p]
         L.pmr446_last_error.restype = C.c_char_p
         L.pmr446_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_ulonglong]

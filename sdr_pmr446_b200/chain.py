@@ -98,6 +98,10 @@ class PmrBatch:
             bufs["ascii"] = np.zeros((S, W), np.uint8)
             bufs["peak"] = np.zeros((S, 2), np.float32)
             bufs["psd"] = np.zeros((S, 4 * W), np.float32)
+        if "rssi" in want:
+            bufs["rssi"] = np.zeros((S, M), np.float32)
+        if "chan_edge" in want:
+            bufs["chan_edge"] = np.zeros((S, M, 2), np.complex64)
         for k, v in bufs.items():
             setattr(out, k, v.ctypes.data)
         ny, ns = C.c_uint(0), C.c_uint(0)
@@ -124,7 +128,7 @@ class PmrBatch:
         for k in parts[0]:
             if k in ("ny", "ns"):
                 continue
-            if k in ("ascii", "peak", "psd"):
+            if k in ("ascii", "peak", "psd", "rssi", "chan_edge"):
                 r[k] = np.stack([p[k] for p in parts], axis=1)
             else:
                 r[k] = np.concatenate([p[k] for p in parts], axis=-1)
@@ -138,7 +142,7 @@ class PmrBatch:
         out = Outputs()
         out.ld = int(outputs.get("ld", self.max_ns))
         out.res_ld = int(outputs.get("res_ld", self.max_res))
-        for k in ("res", "chan", "demod", "lpcomp", "audio", "pcm", "ascii", "peak", "psd"):
+        for k in ("res", "chan", "demod", "lpcomp", "audio", "pcm", "ascii", "peak", "psd", "rssi", "chan_edge"):
             t = outputs.get(k)
             if t is not None:
                 setattr(out, k, t.data_ptr())
@@ -219,6 +223,25 @@ class PmrReceiver:
         for k in ("audio", "pcm", "ctcss_in"):
             r[k] = bufs[k][:, :ns.value]
         return r
+
+    def execute_device(self, iq, n, outputs, stream_ptr=None):
+        """iq: torch CUDA tensor [S, row]; outputs: dict name -> torch CUDA tensor laid out as pmr446_rx_outputs
+        ('rssi', 'status' (uint8 [S, sizeof(pmr446_rx_status)]), 'audio', 'pcm', 'ctcss_in', 'ctcss_power', 'ascii', 'peak') plus
+        'ld'.  Asynchronous; returns ns."""
+        import torch
+        out = _lib.RxOutputs()
+        out.ld = int(outputs.get("ld", self.max_ns))
+        for k in ("rssi", "status", "audio", "pcm", "ctcss_in", "ctcss_power", "ascii", "peak"):
+            t = outputs.get(k)
+            if t is not None:
+                setattr(out, k, t.data_ptr())
+        if stream_ptr is None:
+            stream_ptr = torch.cuda.current_stream().cuda_stream
+        ns = C.c_uint(0)
+        stride = iq.stride(0) * iq.element_size()
+        check(lib().pmr446_receiver_execute_device(self.h, iq.data_ptr(), stride, n, C.byref(out), C.byref(ns), C.c_void_p(stream_ptr)),
+              "pmr446_receiver_execute_device")
+        return ns.value
 
     def run(self, iq, chunk=None):
         """Whole capture in chunks -> list of per-chunk dicts."""

@@ -41,6 +41,10 @@ struct ChanParams {
   float2* chan;            // optional: [n_streams][16][chan_ld], column = f - f0
   long long chan_ld;
 };
+struct ChanTaps {          // selector taps, only read by the TAPS instantiation
+  float* mag_part;         // optional: [n_streams][tiles][16] sum of |y| over the owned frames of each tile (RSSI, :330-336)
+  float2* edge;            // optional: [n_streams][16][2] channel sample of the first (f0) and last (f1 - 1) owned frame
+};
 
 constexpr int CH_TL = 136;      // owned frames per tile
 constexpr int CH_BODIES = 10;   // 10 bodies x 14 frames = 140 computed frames, starting 4 before the tile
@@ -75,8 +79,13 @@ constexpr int CH_A_STRIDE = 17;            // float2 per frame row of the branch
 constexpr int CH_B_STRIDE = 29;            // float2 per channel row of the channel-output buffer (1 previous + 28)
 constexpr int CH_SMEM_WARP = CH_BATCH * CH_A_STRIDE + 16 * CH_B_STRIDE;
 
-template <bool NCO_CONST>
-__global__ void __launch_bounds__(128, 5) channelize16_kernel(ChanParams p) {
+template <bool TAPS> struct TapState { float macc = 0.0f; int k_first = -1, k_last = -1; };
+template <> struct TapState<false> {};
+
+// TAPS = the selector taps (mag_part / edge) are wanted: a separate instantiation, so that the throughput path carries
+// none of their registers.
+template <bool NCO_CONST, bool TAPS>
+__global__ void __launch_bounds__(128, TAPS ? 4 : 5) channelize16_kernel(ChanParams p, ChanTaps tp) {
   __shared__ float2 ch_smem[4 * CH_SMEM_WARP];
   const int lane = threadIdx.x & 31, br = lane & 15, hsel = lane >> 4;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -147,6 +156,11 @@ __global__ void __launch_bounds__(128, 5) channelize16_kernel(ChanParams p) {
   const int k_zero = (fs <= 0 && fs > -4096) ? (int)(-fs) : -1;
   if (lane < 16) B[lane * CH_B_STRIDE] = make_float2(0.0f, 0.0f);   // "previous frame" of the first batch (never owned)
 
+  TapState<TAPS> ta;
+  if constexpr (TAPS) {
+    ta.k_first = (int)(p.f0 - fs > 4096 ? -1 : (p.f0 - fs < 0 ? -1 : p.f0 - fs));
+    ta.k_last = (int)(p.f1 - 1 - fs > 4096 ? -1 : (p.f1 - 1 - fs < 0 ? -1 : p.f1 - 1 - fs));
+  }
   float2 n0 = fetch(0), n1 = fetch(1);
 #pragma unroll 1
   for (int batch = 0; batch < CH_NB; batch++) {
@@ -207,6 +221,19 @@ __global__ void __launch_bounds__(128, 5) channelize16_kernel(ChanParams p) {
         const float im1 = __fsub_rn(__fmul_rn(p1.x, y1.y), __fmul_rn(p1.y, y1.x));
         const float2 dm = make_float2(fast_atan2f(im0, re0) * p.ref, fast_atan2f(im1, re1) * p.ref);
         const int k = k0 + i;
+        if constexpr (TAPS) {
+          if (tp.mag_part) {
+            if (k >= own_lo && k < own_hi) ta.macc += sqrtf(fmaf(y0.x, y0.x, y0.y * y0.y));
+            if (k + 1 >= own_lo && k + 1 < own_hi) ta.macc += sqrtf(fmaf(y1.x, y1.x, y1.y * y1.y));
+          }
+          if (tp.edge) {
+            float2* e = tp.edge + ((long long)s * 16 + br) * 2;
+            if (k == ta.k_first) e[0] = y0;
+            if (k + 1 == ta.k_first) e[0] = y1;
+            if (k == ta.k_last) e[1] = y0;
+            if (k + 1 == ta.k_last) e[1] = y1;
+          }
+        }
         float* d = drow + ((fs32 + (unsigned)k) & dmask);
         if (all) {
           *(float2*)d = dm;
@@ -227,6 +254,22 @@ __global__ void __launch_bounds__(128, 5) channelize16_kernel(ChanParams p) {
     }
     __syncwarp();
   }
+  if constexpr (TAPS) {
+    if (tp.mag_part) {
+      const float m = ta.macc + __shfl_xor_sync(0xffffffffu, ta.macc, 16);
+      if (hsel == 0) tp.mag_part[((long long)s * p.tiles + (warp % p.tiles)) * 16 + br] = m;
+    }
+  }
+}
+
+// rssi[s][c] = 20 log10(sum over the tiles of mag_part / ns): average_power() of the reference for every channel
+static __global__ void rssi_finalize_kernel(const float* mag_part, int tiles, int rows, long long ns, float* rssi) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;   // r = s * 16 + c
+  if (r >= rows) return;
+  const float* m = mag_part + (long long)(r >> 4) * tiles * 16 + (r & 15);
+  float acc = 0.0f;
+  for (int t = 0; t < tiles; t++) acc += m[(long long)t * 16];
+  rssi[r] = 20.0f * log10f(acc / (float)ns);
 }
 
 }  // namespace pmr

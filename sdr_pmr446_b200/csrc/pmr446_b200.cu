@@ -48,6 +48,10 @@ struct pmr446_batch {
   // audio
   DevBuf d_hp, d_lp;
   int hp_chunks = 0, lp_chunks = 0, hp_delay = 0;
+  DevBuf d_mag;              // [S][max_tiles][16] per-tile sums of |chan| (RSSI)
+  int max_tiles = 0;
+  long long last_f0 = 0, last_ns = 0;   // frame range of the last execute call (pmr446_batch_gather_channel)
+  DevBuf d_out_rssi, d_out_edge;
   bool fft_audio = false;    // audio / pcm by fast convolution (audio_fft_kernel); the direct-form kernel serves lpcomp
   DevBuf d_resp, d_aftw;
   // waterfall
@@ -159,6 +163,8 @@ extern "C" int pmr446_batch_create(const pmr446_config* cfg, pmr446_batch** out)
     cudaFuncSetAttribute(channelize_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
 
+  b->max_tiles = (int)(b->max_ns / CH_TL + 3);
+  if (!b->generic && (rc = b->d_mag.alloc_zero((size_t)S * b->max_tiles * 16 * sizeof(float)))) { pmr446_batch_destroy(b); return rc; }
   // demod ring: history for the audio FIR halo + one chunk
   b->demod_cap = next_pow2(b->max_ns + std::max(AU_MAXHALO + AU_LEAD_LP, AF_N) + 64);
   if ((rc = b->d_demod.alloc_zero((size_t)S * M * b->demod_cap * sizeof(float)))) { pmr446_batch_destroy(b); return rc; }
@@ -257,6 +263,25 @@ extern "C" long long pmr446_batch_max_res(const pmr446_batch* b) { return b ? b-
 extern "C" long long pmr446_batch_max_ns(const pmr446_batch* b) { return b ? b->max_ns : 0; }
 extern "C" int pmr446_batch_last_launches(const pmr446_batch* b) { return b ? b->launches : 0; }
 
+static __global__ void gather_channel_kernel(const float* ring, long long stride, long long mask, int M, long long f0, long long ns, const int* channel,
+                                             float* out, long long ld) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = blockIdx.y, c = channel[s];
+  if (k >= ns || c < 0 || c >= M) return;
+  out[(long long)s * ld + k] = ring[((long long)s * M + c) * stride + ((f0 + k) & mask)];
+}
+
+extern "C" int pmr446_batch_gather_channel(pmr446_batch* b, const int* channel, float* demod_out, long long ld, void* cuda_stream) {
+  if (!b || !channel || !demod_out) return fail(PMR446_EINVAL, "null argument");
+  if (b->last_ns > ld) return fail(PMR446_ERANGE, "ld too small");
+  if (b->last_ns == 0) return PMR446_OK;
+  cudaSetDevice(b->device);
+  gather_channel_kernel<<<dim3((unsigned)((b->last_ns + 255) / 256), b->S), 256, 0, (cudaStream_t)cuda_stream>>>(
+      (const float*)b->d_demod.p, b->demod_cap, b->demod_cap - 1, b->M, b->last_f0, b->last_ns, channel, demod_out, ld);
+  CUDA_TRY(cudaGetLastError());
+  return PMR446_OK;
+}
+
 extern "C" int pmr446_batch_timing(pmr446_batch* b, int enable) {
   if (!b) return fail(PMR446_EINVAL, "null handle");
   cudaSetDevice(b->device);
@@ -309,6 +334,9 @@ extern "C" int pmr446_batch_execute_device(pmr446_batch* b, const void* iq, long
   const long long f0 = r0 / M, f1 = r1 / M, ns = f1 - f0;  // frames: cbuffer carry of r % M samples (:804)
   if (out->res && ny > out->res_ld) return fail(PMR446_ERANGE, "res_ld too small");
   if ((out->chan || out->demod || out->lpcomp || out->audio || out->pcm) && ns > out->ld) return fail(PMR446_ERANGE, "ld too small");
+  if ((out->rssi || out->chan_edge) && b->generic) return fail(PMR446_EINVAL, "rssi / chan_edge outputs need the 16-channel kernel");
+  b->last_f0 = f0;
+  b->last_ns = ns;
 
   if (out->res && ny > 0) {
     gather_ring_kernel<float2><<<dim3((unsigned)((ny + 255) / 256), S), 256, 0, st>>>((const float2*)b->fe.out.p, b->fe.out_cap, b->fe.out_cap - 1,
@@ -368,12 +396,26 @@ extern "C" int pmr446_batch_execute_device(pmr446_batch* b, const void* iq, long
     cp.demod_mask = b->demod_cap - 1;
     cp.chan = (float2*)out->chan;
     cp.chan_ld = out->ld;
+    ChanTaps tp;
+    tp.mag_part = out->rssi ? (float*)b->d_mag.p : nullptr;
+    tp.edge = (float2*)out->chan_edge;
+    if (cp.tiles > b->max_tiles) return fail(PMR446_ERANGE, "internal: tile count exceeds allocation");
     long long warps = (long long)S * cp.tiles;   // one warp per (stream, frame tile)
     unsigned blocks = (unsigned)((warps * 32 + 127) / 128);
-    if (b->nco_lut) channelize16_kernel<true><<<blocks, 128, 0, st>>>(cp);
-    else channelize16_kernel<false><<<blocks, 128, 0, st>>>(cp);
+    const bool taps = tp.mag_part || tp.edge;
+    if (b->nco_lut && !taps) channelize16_kernel<true, false><<<blocks, 128, 0, st>>>(cp, tp);
+    else if (b->nco_lut) channelize16_kernel<true, true><<<blocks, 128, 0, st>>>(cp, tp);
+    else if (!taps) channelize16_kernel<false, false><<<blocks, 128, 0, st>>>(cp, tp);
+    else channelize16_kernel<false, true><<<blocks, 128, 0, st>>>(cp, tp);
     b->launches++;
+    if (out->rssi) {
+      rssi_finalize_kernel<<<(S * 16 + 127) / 128, 128, 0, st>>>((const float*)b->d_mag.p, cp.tiles, S * 16, ns, out->rssi);
+      b->launches++;
+    }
     b->timer.mark(st, TM_CHANNELIZE);
+  } else if (out->rssi) {   // empty window: 0 / 0 like the reference's average_power()
+    rssi_finalize_kernel<<<(S * 16 + 127) / 128, 128, 0, st>>>((const float*)b->d_mag.p, 0, S * 16, 0, out->rssi);
+    b->launches++;
   }
   if (ns > 0) {
     if (out->demod) {
@@ -464,7 +506,8 @@ extern "C" int pmr446_batch_execute(pmr446_batch* b, const void* iq, long long i
   // the kernels of sub-chunk k (all filter state carries across execute_device calls, so the result is the
   // same).  Not done when a waterfall row is requested: asgram produces one row per call (:911-912).
   const bool want_wf = W && (out->ascii || out->peak || out->psd);
-  const unsigned K = (!want_wf && n >= 8u * 65536u) ? 8u : 1u;
+  const bool want_sel = out->rssi || out->chan_edge;   // one call = one RSSI window: no time slices
+  const unsigned K = (!want_wf && !want_sel && n >= 8u * 65536u) ? 8u : 1u;
   const unsigned sub = K == 1 ? n : ((n + K - 1) / K + 255u) / 256u * 256u;
   const long long pitch = ((long long)(sub ? sub : 1) * (long long)bps + 255) / 256 * 256;
   int rc;
@@ -488,6 +531,8 @@ extern "C" int pmr446_batch_execute(pmr446_batch* b, const void* iq, long long i
   d.ascii = (char*)stage(W ? out->ascii : nullptr, b->d_out_ascii, (size_t)S * W);
   d.peak = (float*)stage(W ? out->peak : nullptr, b->d_out_peak, (size_t)S * 2 * 4);
   d.psd = (float*)stage(W ? out->psd : nullptr, b->d_out_psd, (size_t)S * 4 * W * 4);
+  d.rssi = (float*)stage(out->rssi, b->d_out_rssi, (size_t)S * M * 4);
+  d.chan_edge = (float*)stage(out->chan_edge, b->d_out_edge, (size_t)S * M * 2 * 8);
   unsigned ny_tot = 0, ns_tot = 0;
   int launches = 0;
   unsigned off = 0;
@@ -544,6 +589,8 @@ extern "C" int pmr446_batch_execute(pmr446_batch* b, const void* iq, long long i
   b->launches = launches;
   const unsigned ny = ny_tot, ns = ns_tot;
   if (K == 1) back_range(st, 0, ny, 0, ns);
+  back(st, out->rssi, d.rssi, M, M, 4, S, 0, M);
+  back(st, out->chan_edge, d.chan_edge, 2 * M, 2 * M, 8, S, 0, 2 * M);
   if (W) {
     back(st, out->ascii, d.ascii, W, W, 1, S, 0, W);
     back(st, out->peak, d.peak, 2, 2, 4, S, 0, 2);

@@ -18,7 +18,8 @@ struct pmr446_receiver {
   pmr446_batch* batch = nullptr;
   int S = 0, M = 0, device = 0;
   long long max_ns = 0, sel_cap = 0;
-  DevBuf d_chan, d_rssi, d_state, d_u, d_range, d_sel, d_lpcomp, d_hp, d_lp, d_coef, d_freqs;
+  DevBuf d_chan, d_rssi, d_state, d_u, d_range, d_sel, d_lpcomp, d_hp, d_lp, d_coef, d_freqs, d_edge, d_selchan, d_selrow;
+  bool fused = false;        // 16-channel kernel: RSSI and edge samples come out of the channelizer, no [S][M][ns] buffer
   int hp_chunks = 0, lp_chunks = 0, hp_delay = 0;
   // staging for the host-buffer call
   DevBuf d_in, d_o_rssi, d_o_status, d_o_audio, d_o_pcm, d_o_ctcss_in, d_o_power, d_o_ascii, d_o_peak;
@@ -93,7 +94,10 @@ extern "C" int pmr446_receiver_create(const pmr446_rx_config* cfg, pmr446_receiv
   float coef[RX_TONES];
   const double fs_audio = (double)cfg->chain.channel_width;
   for (int j = 0; j < RX_TONES; j++) coef[j] = 2.0f * cosf((float)((2.0 * M_PI * pmr446_ctcss_freqs[j]) / fs_audio));
-  if ((rc = r->d_chan.alloc((size_t)S * M * r->max_ns * sizeof(float2))) || (rc = r->d_rssi.alloc_zero((size_t)S * M * sizeof(float))) ||
+  r->fused = (M == 16 && cfg->chain.pfb_m == 13);
+  if ((rc = r->fused ? (r->d_edge.alloc_zero((size_t)S * M * 2 * sizeof(float2)) || r->d_selchan.alloc_zero((size_t)S * sizeof(int)) ||
+                        r->d_selrow.alloc((size_t)S * r->max_ns * sizeof(float)))
+                     : (r->d_selchan.alloc_zero((size_t)S * sizeof(int)) || r->d_chan.alloc((size_t)S * M * r->max_ns * sizeof(float2)))) || (rc = r->d_rssi.alloc_zero((size_t)S * M * sizeof(float))) ||
       (rc = r->d_state.alloc((size_t)S * sizeof(RxState))) || (rc = r->d_u.alloc((size_t)S * 3 * RX_TONES * sizeof(float))) ||
       (rc = r->d_range.alloc_zero((size_t)S * 2 * sizeof(long long))) || (rc = r->d_sel.alloc((size_t)S * r->sel_cap * sizeof(float))) ||
       (rc = r->d_lpcomp.alloc((size_t)S * r->max_ns * sizeof(float))) || (rc = upload_padded(hpt, hpn, r->d_hp, &r->hp_chunks)) ||
@@ -141,7 +145,9 @@ extern "C" int pmr446_receiver_execute_device(pmr446_receiver* r, const void* iq
   // front half: DC block .. channelizer, channel samples kept in d_chan [S][M][max_ns]
   pmr446_outputs bo;
   memset(&bo, 0, sizeof bo);
-  bo.chan = (float*)r->d_chan.p;
+  bo.chan = r->fused ? nullptr : (float*)r->d_chan.p;
+  bo.rssi = r->fused ? (float*)r->d_rssi.p : nullptr;
+  bo.chan_edge = r->fused ? (float*)r->d_edge.p : nullptr;
   bo.ld = r->max_ns;
   bo.ascii = out->ascii;
   bo.peak = out->peak;
@@ -153,13 +159,14 @@ extern "C" int pmr446_receiver_execute_device(pmr446_receiver* r, const void* iq
 
   float* rssi = (float*)r->d_rssi.p;
   RxState* state = (RxState*)r->d_state.p;
-  rssi_kernel<<<S * M, 128, 0, st>>>((const float2*)r->d_chan.p, r->max_ns, (int)ns, rssi);
+  if (!r->fused) rssi_kernel<<<S * M, 128, 0, st>>>((const float2*)r->d_chan.p, r->max_ns, (int)ns, rssi);
   if (out->rssi) CUDA_TRY(cudaMemcpyAsync(out->rssi, rssi, (size_t)S * M * sizeof(float), cudaMemcpyDeviceToDevice, st));
   SquelchParams sp;
   sp.rssi = rssi;
   sp.st = state;
   sp.u = (float*)r->d_u.p;
   sp.sel_range = (long long*)r->d_range.p;
+  sp.sel_chan = (int*)r->d_selchan.p;
   sp.S = S;
   sp.M = M;
   sp.ns = (int)ns;
@@ -169,9 +176,16 @@ extern "C" int pmr446_receiver_execute_device(pmr446_receiver* r, const void* iq
   squelch_kernel<<<(S + 127) / 128, 128, 0, st>>>(sp);
   r->launches += 2;
   if (ns > 0) {
-    rx_demod_kernel<<<dim3((ns + 255) / 256, S), 256, 0, st>>>((const float2*)r->d_chan.p, r->max_ns, M, (int)ns, state,
-                                                                 1.0f / (2 * (float)M_PI * r->cfg.chain.kf), (float*)r->d_sel.p, r->sel_cap,
-                                                                 r->sel_cap - 1);
+    const float ref = 1.0f / (2 * (float)M_PI * r->cfg.chain.kf);
+    if (r->fused) {
+      if ((rc = pmr446_batch_gather_channel(r->batch, (const int*)r->d_selchan.p, (float*)r->d_selrow.p, r->max_ns, st))) return rc;
+      rx_append_kernel<<<dim3((ns + 255) / 256, S), 256, 0, st>>>((const float*)r->d_selrow.p, r->max_ns, (const float2*)r->d_edge.p, M, (int)ns, state,
+                                                                    ref, (float*)r->d_sel.p, r->sel_cap, r->sel_cap - 1);
+      r->launches++;
+    } else {
+      rx_demod_kernel<<<dim3((ns + 255) / 256, S), 256, 0, st>>>((const float2*)r->d_chan.p, r->max_ns, M, (int)ns, state, ref, (float*)r->d_sel.p,
+                                                                   r->sel_cap, r->sel_cap - 1);
+    }
     AudioParams ap;
     memset(&ap, 0, sizeof ap);
     ap.demod = (const float*)r->d_sel.p;

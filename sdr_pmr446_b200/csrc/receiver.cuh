@@ -11,6 +11,7 @@
 #include <stdint.h>
 
 #include "../../include/pmr446_b200.h"
+#include "channelizer.cuh"   // fast_atan2f
 
 namespace pmr {
 
@@ -54,6 +55,7 @@ struct SquelchParams {
   RxState* st;
   float* u;              // [S][3][RX_TONES]: u0, u1, power
   long long* sel_range;  // [S][2] for the audio kernel
+  int* sel_chan;         // [S] active channel after this chunk's update (-1 = none), for pmr446_batch_gather_channel
   int S, M, ns;
   float squelch;
   unsigned long long mask;
@@ -107,6 +109,7 @@ static __global__ void squelch_kernel(SquelchParams p) {
   st.events = ev;
   p.sel_range[2 * s] = st.sel_f0;
   p.sel_range[2 * s + 1] = st.sel_f1;
+  p.sel_chan[s] = st.active;
   p.st[s] = st;
 }
 
@@ -124,6 +127,27 @@ static __global__ void rx_demod_kernel(const float2* chan, long long ld, int M, 
   const float im = __fsub_rn(__fmul_rn(pv.x, y.y), __fmul_rn(pv.y, y.x));
   sel[(long long)s * sel_stride + ((st[s].sel_f0 + k) & sel_mask)] = atan2f(im, re) * ref;
   if (k == ns - 1) st[s].prev_next = y;
+}
+
+// Same append, from the library's discriminator ring: `row` holds the active channel's discriminator output of this call
+// (pmr446_batch_gather_channel).  Only the first sample is recomputed, against the selected demodulator's own r_prime --
+// it differs from the ring's value when the active channel just changed or the demodulator was reset.
+static __global__ void rx_append_kernel(const float* row, long long ld, const float2* edge, int M, int ns, RxState* st, float ref, float* sel,
+                                        long long sel_stride, long long sel_mask) {
+  const int s = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int active = st[s].active;
+  if (active < 0 || k >= ns) return;
+  float v = row[(long long)s * ld + k];
+  const float2* e = edge + ((long long)s * M + active) * 2;
+  if (k == 0) {
+    const float2 y = e[0], pv = st[s].prev_cur;
+    const float re = __fadd_rn(__fmul_rn(pv.x, y.x), __fmul_rn(pv.y, y.y));
+    const float im = __fsub_rn(__fmul_rn(pv.x, y.y), __fmul_rn(pv.y, y.x));
+    v = fast_atan2f(im, re) * ref;
+  }
+  sel[(long long)s * sel_stride + ((st[s].sel_f0 + k) & sel_mask)] = v;
+  if (k == ns - 1) st[s].prev_next = e[1];
 }
 
 struct CtcssParams {

@@ -253,3 +253,35 @@ def test_five_channels_odd_row_count():
             assert rel_rms(g["audio"][s, c, sl], r["audio"][c, sl]) < REL_RMS_TOL, ("audio", s, c)
             dp = np.abs(g["pcm"][s, c, sl].astype(np.int32) - r["pcm"][c, sl].astype(np.int32))
             assert dp.max() <= PCM_TOL_LSB, ("pcm", s, c, int(dp.max()))
+
+
+def test_selector_taps_rssi_and_edge_samples():
+    """rssi / chan_edge outputs of the batch (fused into the channelizer) against the channel samples themselves, and
+    pmr446_batch_gather_channel against the demod output, over several chunks of uneven size."""
+    import ctypes as C
+
+    import torch
+    from sdr_pmr446_b200 import chain, synth
+    from sdr_pmr446_b200._lib import check, lib
+    fs, S = 2400000, 2
+    iq = np.stack([synth.make_cu8(synth.CaptureSpec(fs=float(fs), carriers=synth.rotated_carriers(s)), 500000, 470 + s) for s in range(S)])
+    gpu = chain.PmrBatch(n_streams=S, fs_in=fs, in_fmt=1, audio_gain=1.0, max_chunk=240000)
+    o = 0
+    for n in (240000, 17, 100001, 159982):
+        g = gpu.execute(iq[:, 2 * o:2 * (o + n)], want=("chan", "demod", "rssi", "chan_edge"))
+        o += n
+        ns = g["ns"]
+        if ns == 0:
+            assert np.all(np.isnan(g["rssi"]))
+            continue
+        want = 20 * np.log10(np.mean(np.abs(g["chan"].astype(np.complex128)), axis=2))
+        assert np.max(np.abs(g["rssi"] - want)) < 1e-3
+        assert np.array_equal(g["chan_edge"][:, :, 0], g["chan"][:, :, 0]) and np.array_equal(g["chan_edge"][:, :, 1], g["chan"][:, :, ns - 1])
+        sel = torch.tensor([3, -1], dtype=torch.int32, device="cuda")
+        row = torch.full((S, gpu.max_ns), -7.0, dtype=torch.float32, device="cuda")
+        check(lib().pmr446_batch_gather_channel(gpu.h, sel.data_ptr(), row.data_ptr(), gpu.max_ns, C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+              "pmr446_batch_gather_channel")
+        torch.cuda.synchronize()
+        r = row.cpu().numpy()
+        assert np.array_equal(r[0, :ns], g["demod"][0, 3]) and np.all(r[1] == -7.0)
+    gpu.close()

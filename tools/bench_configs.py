@@ -9,7 +9,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 
-from sdr_pmr446_b200 import chain, synth
+import ctypes as C
+
+from sdr_pmr446_b200 import _lib, chain, synth
 
 
 def timed(fn, steps=3, warm=2):
@@ -60,4 +62,14 @@ pk = torch.empty((S, 2), dtype=torch.float32, device="cuda")
 ms = timed(lambda: b.execute_device(iq.view(torch.float32).view(S, -1), n, {"pcm": pcm, "ld": b.max_ns, "ascii": asc, "peak": pk}))
 out["cfg3_wideband_20M_cf32_1600ch_x4"] = {"ms_per_step": ms, "msps": S * n / ms / 1e3, "realtime_streams": S * n / ms / 1e3 / 20.0}
 b.close()
+# receiver mode (what the reference plays): 1024 x 2.4 Msps, RSSI + squelch + selected-channel audio + CTCSS per stream
+S, fs, n = 1024, 2400000, 2400000
+iq = tiled(synth.make_cu8(synth.CaptureSpec(fs=float(fs)), n, 446), S)
+rx = chain.PmrReceiver(n_streams=S, fs_in=fs, in_fmt=1, max_chunk=n, audio_gain=1.0)
+o = {"ld": rx.max_ns, "pcm": torch.empty((S, rx.max_ns), dtype=torch.int16, device="cuda"),
+     "status": torch.empty((S, C.sizeof(_lib.RxStatus)), dtype=torch.uint8, device="cuda"),
+     "rssi": torch.empty((S, 16), dtype=torch.float32, device="cuda")}
+ms = timed(lambda: rx.execute_device(iq, n, o))
+out["receiver_2400k_cu8_x1024"] = {"ms_per_step": ms, "msps": S * n / ms / 1e3, "launches": rx.last_launches}
+rx.close()
 print(json.dumps(out, indent=1))
