@@ -144,6 +144,153 @@ static __global__ void __launch_bounds__(1024) wf_accumulate_kernel(WfParams p) 
   for (int i = threadIdx.x; i < p.nfft; i += blockDim.x) out[i] = acc[i];
 }
 
+// ---- small transforms (nfft <= 1024): one WARP per transform ----------------------------------------------------------
+// A 480-point transform has 96..240 butterflies per stage: a whole block on one transform leaves most threads idle and
+// pays a block barrier per stage.  Here every warp of the block walks its own transforms (ping-pong buffers private to
+// the warp, __syncwarp between stages, |X|^2 accumulated in registers: bin lane + 32 m), the twiddle table sits in
+// shared memory, and because nfft = 4 W with a leading radix-4 stage whose inputs 1..3 are the zero padding, that stage
+// is the load itself (each windowed sample is written to its four outputs).
+constexpr int WFW_WARPS = 8;   // at most; the launch uses as many as fit in 48 KB of shared memory (no opt-in needed)
+
+template <int R>
+__device__ __forceinline__ void wf_stage_warp(const float2* __restrict__ x, float2* __restrict__ y, const float2* __restrict__ tw, int N, int Ns,
+                                              float inv_ns, int lane) {
+  const int nb = N / R, tstep = N / (Ns * R);
+  for (int j = lane; j < nb; j += 32) {
+    const int k = j - (int)(((float)j + 0.5f) * inv_ns) * Ns;   // j mod Ns (exact for j < 2^20)
+    float2 v[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      float2 a = x[j + r * nb];
+      if (r > 0) {
+        const float2 w = tw[r * k * tstep];   // r k tstep < N
+        a = make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+      }
+      v[r] = a;
+    }
+    const int j0 = (j - k) * R + k;
+    if (R == 2) {
+      y[j0] = make_float2(v[0].x + v[1].x, v[0].y + v[1].y);
+      y[j0 + Ns] = make_float2(v[0].x - v[1].x, v[0].y - v[1].y);
+    } else if (R == 4) {
+      const float2 s02 = make_float2(v[0].x + v[2].x, v[0].y + v[2].y), d02 = make_float2(v[0].x - v[2].x, v[0].y - v[2].y);
+      const float2 s13 = make_float2(v[1].x + v[3].x, v[1].y + v[3].y), d13 = make_float2(v[1].x - v[3].x, v[1].y - v[3].y);
+      y[j0] = make_float2(s02.x + s13.x, s02.y + s13.y);
+      y[j0 + Ns] = make_float2(d02.x + d13.y, d02.y - d13.x);
+      y[j0 + 2 * Ns] = make_float2(s02.x - s13.x, s02.y - s13.y);
+      y[j0 + 3 * Ns] = make_float2(d02.x - d13.y, d02.y + d13.x);
+    } else {
+      const int rstep = N / R;
+#pragma unroll
+      for (int q = 0; q < R; q++) {
+        float2 acc = v[0];
+#pragma unroll
+        for (int r = 1; r < R; r++) {
+          const float2 w = tw[((q * r) % R) * rstep];
+          acc.x += v[r].x * w.x - v[r].y * w.y;
+          acc.y += v[r].x * w.y + v[r].y * w.x;
+        }
+        y[j0 + q * Ns] = acc;
+      }
+    }
+  }
+}
+
+static __global__ void __launch_bounds__(32 * WFW_WARPS) wf_accumulate_warp_kernel(WfParams p) {
+  extern __shared__ float2 wf_smem[];
+  const int N = p.nfft, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float2* tw = wf_smem;                              // [N]
+  float2* a = wf_smem + N + (size_t)w * 2 * N;       // this warp's ping
+  float2* b = a + N;                                 // and pong
+  const int s = blockIdx.x / p.parts, part = blockIdx.x % p.parts;
+  const float2* res = p.res + (long long)s * p.res_stride;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = p.twiddle[i];
+  __syncthreads();
+  float acc[32];
+#pragma unroll
+  for (int m = 0; m < 32; m++) acc[m] = 0.0f;
+  const bool lead4 = p.radix[0] == 4 && N == 4 * p.W;    // first stage folded into the load
+  const int nw = blockDim.x >> 5;
+  for (int t = 1 + part + p.parts * w; t <= p.n_transforms; t += p.parts * nw) {
+    const long long first = (long long)t * p.hop - p.W;  // chunk-local index of window sample 0
+    if (lead4) {
+      for (int i = lane; i < p.W; i += 32) {
+        const long long li = first + i;
+        float2 v = make_float2(0.0f, 0.0f);
+        if (li >= 0) {
+          const float2 x = res[(p.r0 + li) & p.res_mask];
+          const float wv = p.window[i];
+          v = make_float2(x.x * wv, x.y * wv);
+        }
+        b[4 * i] = v; b[4 * i + 1] = v; b[4 * i + 2] = v; b[4 * i + 3] = v;
+      }
+    } else {
+      for (int i = lane; i < N; i += 32) {
+        float2 v = make_float2(0.0f, 0.0f);
+        const long long li = first + i;
+        if (i < p.W && li >= 0) {
+          const float2 x = res[(p.r0 + li) & p.res_mask];
+          const float wv = p.window[i];
+          v = make_float2(x.x * wv, x.y * wv);
+        }
+        a[i] = v;
+      }
+    }
+    __syncwarp();
+    float2 *x = lead4 ? b : a, *y = lead4 ? a : b;
+    int Ns = lead4 ? 4 : 1;
+    for (int st = lead4 ? 1 : 0; st < p.n_stages; st++) {
+      const int R = p.radix[st];
+      const float inv = 1.0f / (float)Ns;
+      if (R == 4) wf_stage_warp<4>(x, y, tw, N, Ns, inv, lane);
+      else if (R == 2) wf_stage_warp<2>(x, y, tw, N, Ns, inv, lane);
+      else if (R == 3) wf_stage_warp<3>(x, y, tw, N, Ns, inv, lane);
+      else if (R == 5) wf_stage_warp<5>(x, y, tw, N, Ns, inv, lane);
+      else {   // other primes: O(R^2) butterfly straight from shared memory
+        const int nb = N / R, tstep = N / (Ns * R), rstep = N / R;
+        for (int j = lane; j < nb; j += 32) {
+          const int k = j % Ns, j0 = (j - k) * R + k;
+          for (int q = 0; q < R; q++) {
+            float2 sum = x[j];
+            for (int r = 1; r < R; r++) {
+              const float2 v = x[j + r * nb];
+              const float2 w1 = tw[r * k * tstep], w2 = tw[((q * r) % R) * rstep];
+              const float2 ww = make_float2(w1.x * w2.x - w1.y * w2.y, w1.x * w2.y + w1.y * w2.x);
+              sum.x += v.x * ww.x - v.y * ww.y;
+              sum.y += v.x * ww.y + v.y * ww.x;
+            }
+            y[j0 + q * Ns] = sum;
+          }
+        }
+      }
+      Ns *= R;
+      float2* tmp = x; x = y; y = tmp;
+      __syncwarp();
+    }
+#pragma unroll
+    for (int m = 0; m < 32; m++) {
+      const int i = lane + 32 * m;
+      if (i < N) acc[m] += x[i].x * x[i].x + x[i].y * x[i].y;
+    }
+    __syncwarp();
+  }
+  // block reduction of the warps' accumulators through the (now idle) transform buffers
+  __syncthreads();
+  float* red = (float*)(wf_smem + N);   // [WFW_WARPS][N]
+#pragma unroll
+  for (int m = 0; m < 32; m++) {
+    const int i = lane + 32 * m;
+    if (i < N) red[(size_t)w * N + i] = acc[m];
+  }
+  __syncthreads();
+  float* out = p.partial + ((long long)s * p.parts + part) * N;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    float sum = 0.0f;
+    for (int q = 0; q < nw; q++) sum += red[(size_t)q * N + i];
+    out[i] = sum;
+  }
+}
+
 struct WfFinalParams {
   const float* partial;
   int parts, W, nfft, n_transforms;
@@ -211,6 +358,8 @@ static __global__ void __launch_bounds__(256) wf_finalize_kernel(WfFinalParams p
   }
 }
 
+// init() and execute() are force-inlined: the kernels above are static (one copy per translation unit), so the code that
+// sets their attributes and launches them must not be merged across translation units by the linker either.
 struct Waterfall {
   int S = 0;
   unsigned W = 0, nfft = 0;
@@ -219,8 +368,10 @@ struct Waterfall {
   std::vector<int> radix;
   DevBuf d_window, d_twiddle, d_partial, d_scratch;
   size_t smem = 0;
+  bool warp_kernel = false;   // nfft <= 1024: one warp per transform
+  int wf_warps = 1;
 
-  int init(int n_streams, unsigned width) {
+  __attribute__((always_inline)) inline int init(int n_streams, unsigned width) {
     S = n_streams;
     W = width;
     nfft = 4 * width;
@@ -240,9 +391,12 @@ struct Waterfall {
       double a = -2.0 * M_PI * (double)k / (double)nfft;
       tw[k] = make_float2((float)cos(a), (float)sin(a));
     }
-    // enough (stream, part) blocks to fill the GPU: one block needs nfft * 20 bytes of shared memory
+    // enough (stream, part) blocks to fill the GPU: one block needs nfft * 20 bytes of shared memory (block-per-transform
+    // kernel) or nfft * 8 * (1 + 2 * 8 warps) bytes (warp-per-transform kernel, nfft <= 1024)
+    warp_kernel = nfft <= 1024;
+    wf_warps = std::max(1, std::min(WFW_WARPS, (int)((48 * 1024 / (nfft * sizeof(float2)) - 1) / 2)));
     {
-      const size_t per_block = (size_t)nfft * (2 * sizeof(float2) + sizeof(float));
+      const size_t per_block = warp_kernel ? (size_t)nfft * sizeof(float2) * (1 + 2 * wf_warps) : (size_t)nfft * (2 * sizeof(float2) + sizeof(float));
       const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / per_block));
       parts = std::max(1, std::min(128, (148 * per_sm + S - 1) / S));
     }
@@ -252,12 +406,13 @@ struct Waterfall {
       return rc;
     CUDA_TRY(cudaMemcpy(d_window.p, w.data(), W * sizeof(float), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d_twiddle.p, tw.data(), nfft * sizeof(float2), cudaMemcpyHostToDevice));
-    smem = (size_t)nfft * (2 * sizeof(float2) + sizeof(float));
-    CUDA_TRY(cudaFuncSetAttribute(wf_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem = warp_kernel ? (size_t)nfft * sizeof(float2) * (1 + 2 * wf_warps) : (size_t)nfft * (2 * sizeof(float2) + sizeof(float));
+    if (!warp_kernel) CUDA_TRY(cudaFuncSetAttribute(wf_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return 0;
   }
 
-  int execute(const float2* res, long long res_cap, long long r0, long long ny, char* ascii, float* peak, float* psd, cudaStream_t st,
+  __attribute__((always_inline)) inline int execute(const float2* res, long long res_cap, long long r0, long long ny, char* ascii, float* peak,
+                                                    float* psd, cudaStream_t st,
               int* launches) {
     WfParams p;
     p.res = res;
@@ -277,7 +432,8 @@ struct Waterfall {
     p.partial = (float*)d_partial.p;
     if (p.n_transforms > 0) {
       // a large transform leaves room for one block per SM only: give it 32 warps to hide the shared-memory latency
-      wf_accumulate_kernel<<<S * parts, smem > 48 * 1024 ? 1024 : 256, smem, st>>>(p);
+      if (warp_kernel) wf_accumulate_warp_kernel<<<S * parts, 32 * wf_warps, smem, st>>>(p);
+      else wf_accumulate_kernel<<<S * parts, smem > 48 * 1024 ? 1024 : 256, smem, st>>>(p);
       (*launches)++;
     }
     WfFinalParams f;
