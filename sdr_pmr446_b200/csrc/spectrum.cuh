@@ -33,6 +33,31 @@ struct WfParams {
   float* partial;          // [n_streams][parts][nfft]
 };
 
+// forward DFTs of 3 and 5 points with constant coefficients (in place: v[q] <- sum_r v[r] W_R^(q r))
+__device__ __forceinline__ void dft3(float2* v) {
+  const float s = 0.86602540378443865f;
+  const float2 t1 = make_float2(v[1].x + v[2].x, v[1].y + v[2].y);
+  const float2 t2 = make_float2(fmaf(-0.5f, t1.x, v[0].x), fmaf(-0.5f, t1.y, v[0].y));
+  const float2 t3 = make_float2(s * (v[1].x - v[2].x), s * (v[1].y - v[2].y));
+  v[0] = make_float2(v[0].x + t1.x, v[0].y + t1.y);
+  v[1] = make_float2(t2.x + t3.y, t2.y - t3.x);   // t2 - i t3
+  v[2] = make_float2(t2.x - t3.y, t2.y + t3.x);   // t2 + i t3
+}
+__device__ __forceinline__ void dft5(float2* v) {
+  const float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f, s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;
+  const float2 a1 = make_float2(v[1].x + v[4].x, v[1].y + v[4].y), a2 = make_float2(v[2].x + v[3].x, v[2].y + v[3].y);
+  const float2 b1 = make_float2(v[1].x - v[4].x, v[1].y - v[4].y), b2 = make_float2(v[2].x - v[3].x, v[2].y - v[3].y);
+  const float2 p1 = make_float2(fmaf(c2, a2.x, fmaf(c1, a1.x, v[0].x)), fmaf(c2, a2.y, fmaf(c1, a1.y, v[0].y)));
+  const float2 p2 = make_float2(fmaf(c1, a2.x, fmaf(c2, a1.x, v[0].x)), fmaf(c1, a2.y, fmaf(c2, a1.y, v[0].y)));
+  const float2 q1 = make_float2(fmaf(s2, b2.x, s1 * b1.x), fmaf(s2, b2.y, s1 * b1.y));
+  const float2 q2 = make_float2(fmaf(-s1, b2.x, s2 * b1.x), fmaf(-s1, b2.y, s2 * b1.y));
+  v[0] = make_float2(v[0].x + a1.x + a2.x, v[0].y + a1.y + a2.y);
+  v[1] = make_float2(p1.x + q1.y, p1.y - q1.x);   // p1 - i q1
+  v[4] = make_float2(p1.x - q1.y, p1.y + q1.x);   // p1 + i q1
+  v[2] = make_float2(p2.x + q2.y, p2.y - q2.x);   // p2 - i q2
+  v[3] = make_float2(p2.x - q2.y, p2.y + q2.x);   // p2 + i q2
+}
+
 template <int R>
 __device__ __forceinline__ void wf_stage(const float2* __restrict__ x, float2* __restrict__ y, const float2* __restrict__ tw, int N, int Ns) {
   const int nb = N / R;
@@ -62,18 +87,10 @@ __device__ __forceinline__ void wf_stage(const float2* __restrict__ x, float2* _
       y[j0 + 2 * Ns] = make_float2(s02.x - s13.x, s02.y - s13.y);
       y[j0 + 3 * Ns] = make_float2(d02.x - d13.y, d02.y + d13.x);  // d02 + i d13
     } else {
-      const int rstep = N / R;
+      if (R == 3) dft3(v);
+      else dft5(v);
 #pragma unroll
-      for (int q = 0; q < R; q++) {
-        float2 acc = v[0];
-#pragma unroll
-        for (int r = 1; r < R; r++) {
-          const float2 w = tw[((q * r) % R) * rstep];
-          acc.x += v[r].x * w.x - v[r].y * w.y;
-          acc.y += v[r].x * w.y + v[r].y * w.x;
-        }
-        y[j0 + q * Ns] = acc;
-      }
+      for (int q = 0; q < R; q++) y[j0 + q * Ns] = v[q];
     }
   }
 }
@@ -180,22 +197,15 @@ __device__ __forceinline__ void wf_stage_warp(const float2* __restrict__ x, floa
       y[j0 + 2 * Ns] = make_float2(s02.x - s13.x, s02.y - s13.y);
       y[j0 + 3 * Ns] = make_float2(d02.x - d13.y, d02.y + d13.x);
     } else {
-      const int rstep = N / R;
+      if (R == 3) dft3(v);
+      else dft5(v);
 #pragma unroll
-      for (int q = 0; q < R; q++) {
-        float2 acc = v[0];
-#pragma unroll
-        for (int r = 1; r < R; r++) {
-          const float2 w = tw[((q * r) % R) * rstep];
-          acc.x += v[r].x * w.x - v[r].y * w.y;
-          acc.y += v[r].x * w.y + v[r].y * w.x;
-        }
-        y[j0 + q * Ns] = acc;
-      }
+      for (int q = 0; q < R; q++) y[j0 + q * Ns] = v[q];
     }
   }
 }
 
+template <int NM>   // accumulator registers per lane: nfft <= 32 NM
 static __global__ void __launch_bounds__(32 * WFW_WARPS) wf_accumulate_warp_kernel(WfParams p) {
   extern __shared__ float2 wf_smem[];
   const int N = p.nfft, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -206,9 +216,9 @@ static __global__ void __launch_bounds__(32 * WFW_WARPS) wf_accumulate_warp_kern
   const float2* res = p.res + (long long)s * p.res_stride;
   for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = p.twiddle[i];
   __syncthreads();
-  float acc[32];
+  float acc[NM];
 #pragma unroll
-  for (int m = 0; m < 32; m++) acc[m] = 0.0f;
+  for (int m = 0; m < NM; m++) acc[m] = 0.0f;
   const bool lead4 = p.radix[0] == 4 && N == 4 * p.W;    // first stage folded into the load
   const int nw = blockDim.x >> 5;
   for (int t = 1 + part + p.parts * w; t <= p.n_transforms; t += p.parts * nw) {
@@ -268,9 +278,9 @@ static __global__ void __launch_bounds__(32 * WFW_WARPS) wf_accumulate_warp_kern
       __syncwarp();
     }
 #pragma unroll
-    for (int m = 0; m < 32; m++) {
+    for (int m = 0; m < NM; m++) {
       const int i = lane + 32 * m;
-      if (i < N) acc[m] += x[i].x * x[i].x + x[i].y * x[i].y;
+      if (i < N) { const float2 z = x[i]; acc[m] = fmaf(z.x, z.x, fmaf(z.y, z.y, acc[m])); }
     }
     __syncwarp();
   }
@@ -278,7 +288,7 @@ static __global__ void __launch_bounds__(32 * WFW_WARPS) wf_accumulate_warp_kern
   __syncthreads();
   float* red = (float*)(wf_smem + N);   // [WFW_WARPS][N]
 #pragma unroll
-  for (int m = 0; m < 32; m++) {
+  for (int m = 0; m < NM; m++) {
     const int i = lane + 32 * m;
     if (i < N) red[(size_t)w * N + i] = acc[m];
   }
@@ -432,7 +442,9 @@ struct Waterfall {
     p.partial = (float*)d_partial.p;
     if (p.n_transforms > 0) {
       // a large transform leaves room for one block per SM only: give it 32 warps to hide the shared-memory latency
-      if (warp_kernel) wf_accumulate_warp_kernel<<<S * parts, 32 * wf_warps, smem, st>>>(p);
+      if (warp_kernel && nfft <= 256) wf_accumulate_warp_kernel<8><<<S * parts, 32 * wf_warps, smem, st>>>(p);
+      else if (warp_kernel && nfft <= 512) wf_accumulate_warp_kernel<16><<<S * parts, 32 * wf_warps, smem, st>>>(p);
+      else if (warp_kernel) wf_accumulate_warp_kernel<32><<<S * parts, 32 * wf_warps, smem, st>>>(p);
       else wf_accumulate_kernel<<<S * parts, smem > 48 * 1024 ? 1024 : 256, smem, st>>>(p);
       (*launches)++;
     }
