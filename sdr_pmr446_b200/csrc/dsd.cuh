@@ -26,23 +26,52 @@ static __global__ void dsd_freqdem_kernel(const float2* res, long long res_strid
 }
 
 // arbitrary resampler on a real ring (A.5): z[k] = sum_t pfb[idx_k][t] * fm[i_k - t],
-// i_k = floor(k*step / 2^24), idx_k = (k*step mod 2^24) >> (24 - bits)
-static __global__ void dsd_arb_kernel(const float* fm, long long fm_stride, long long fm_mask, float* z, long long z_stride, long long z_mask,
-                               long long k0, long long k1, unsigned step, int bits, const float* pfb) {
-  const long long k = k0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= k1) return;
+// i_k = floor(k*step / 2^24), idx_k = (k*step mod 2^24) >> (24 - bits).
+// One block = 256 consecutive outputs of one stream: their inputs and the filter bank (rows 20 floats apart, see
+// cascade_kernel) are staged in shared memory, so an output costs 4 LDS.128 + 14 LDS.32 + 14 FFMA.
+constexpr int DSD_XS = 576;   // inputs staged per block: enough for 256 outputs at any step <= 2^25
+static __global__ void __launch_bounds__(256) dsd_arb_kernel(const float* fm, long long fm_stride, long long fm_mask, float* z, long long z_stride,
+                                                             long long z_mask, long long k0, long long k1, unsigned step, int bits, const float* pfb) {
+  __shared__ float xs[DSD_XS];
+  __shared__ __align__(16) float bank[256 * 20];
   const int s = blockIdx.y;
+  const long long kb = k0 + (long long)blockIdx.x * 256;
+  const long long kend = kb + 256 < k1 ? kb + 256 : k1;
+  if (kb >= k1) return;
+  const float* f = fm + (long long)s * fm_stride;
+  const long long i_first = (long long)(((unsigned long long)kb * step) >> 24) - 13;
+  const long long i_last = (long long)(((unsigned long long)(kend - 1) * step) >> 24);
+  const int count = (int)(i_last - i_first + 1);
+  const bool staged = count <= DSD_XS && bits <= 8;   // block-uniform
+  if (staged) {
+    for (int c = threadIdx.x; c < count; c += 256) {
+      const long long n = i_first + c;
+      xs[c] = n >= 0 ? f[n & fm_mask] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < (16 << bits); i += 256) bank[(i >> 4) * 20 + (i & 15)] = __ldg(pfb + i);
+  }
+  __syncthreads();
+  const long long k = kb + threadIdx.x;
+  if (k >= kend) return;
   const unsigned long long ph = (unsigned long long)k * step;
   const long long i = (long long)(ph >> 24);
   const unsigned idx = (unsigned)(ph & 0xffffffu) >> (24 - bits);
-  const float* row = pfb + ((size_t)idx << 4);
-  const float* f = fm + (long long)s * fm_stride;
   float acc = 0.0f;
+  if (staged) {
+    const float4* row = (const float4*)(bank + idx * 20);
+    const float4 h0 = row[0], h1 = row[1], h2 = row[2], h3 = row[3];
+    const float h[14] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w, h2.x, h2.y, h2.z, h2.w, h3.x, h3.y};
+    const float* x = xs + (int)(i - i_first);
 #pragma unroll
-  for (int t = 0; t < 14; t++) {
-    const long long n = i - t;
-    const float v = n >= 0 ? f[n & fm_mask] : 0.0f;
-    acc = fmaf(__ldg(row + t), v, acc);
+    for (int t = 0; t < 14; t++) acc = fmaf(h[t], x[-t], acc);
+  } else {
+    const float* row = pfb + ((size_t)idx << 4);
+#pragma unroll
+    for (int t = 0; t < 14; t++) {
+      const long long n = i - t;
+      const float v = n >= 0 ? f[n & fm_mask] : 0.0f;
+      acc = fmaf(__ldg(row + t), v, acc);
+    }
   }
   z[(long long)s * z_stride + (k & z_mask)] = acc;
 }
@@ -58,27 +87,38 @@ struct DsdInterpParams {
   short* pcm;        // optional [n_streams][out_ld]
   long long out_ld;
 };
-static __global__ void dsd_interp_kernel(DsdInterpParams p) {
-  const long long k = p.k0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= p.k1) return;
+// one block = 256 consecutive input positions k of one stream, staged with their 2m - 1 predecessors
+static __global__ void __launch_bounds__(256) dsd_interp_kernel(DsdInterpParams p) {
+  __shared__ float zs[256 + 20];
   const int s = blockIdx.y;
+  const long long kb = p.k0 + (long long)blockIdx.x * 256;
+  if (kb >= p.k1) return;
   const float* z = p.z + (long long)s * p.z_stride;
-  const long long d = k - p.m;
-  const float y0 = d >= 0 ? z[d & p.z_mask] : 0.0f;
-  float y1 = 0.0f;
-  for (int j = 0; j < 2 * p.m; j++) {
-    const long long n = k - j;
-    const float v = n >= 0 ? z[n & p.z_mask] : 0.0f;
-    y1 = fmaf(p.hb[j], v, y1);
+  const int hist = 2 * p.m - 1;
+  for (int c = threadIdx.x; c < 256 + hist; c += 256) {
+    const long long n = kb - hist + c;
+    zs[c] = (n >= 0 && n < p.k1) ? z[n & p.z_mask] : 0.0f;
   }
-  const long long o = 2 * (k - p.k0);
+  __syncthreads();
+  const long long k = kb + threadIdx.x;
+  if (k >= p.k1) return;
+  const float* q = zs + threadIdx.x + hist;   // q[-j] = z[k - j]
+  const float y0 = q[-p.m];
+  float y1 = 0.0f;
+  for (int j = 0; j < 2 * p.m; j++) y1 = fmaf(p.hb[j], q[-j], y1);
+  const long long o = (long long)s * p.out_ld + 2 * (k - p.k0);
   if (p.audio) {
-    p.audio[(long long)s * p.out_ld + o] = y0;
-    p.audio[(long long)s * p.out_ld + o + 1] = y1;
+    p.audio[o] = y0;
+    p.audio[o + 1] = y1;
   }
   if (p.pcm) {
-    p.pcm[(long long)s * p.out_ld + o] = (short)__float2int_rz(y0 * 32767.0f);
-    p.pcm[(long long)s * p.out_ld + o + 1] = (short)__float2int_rz(y1 * 32767.0f);
+    const short a = (short)__float2int_rz(y0 * 32767.0f), b = (short)__float2int_rz(y1 * 32767.0f);
+    if (((o | (long long)(uintptr_t)p.pcm >> 1) & 1) == 0) {
+      *(short2*)(p.pcm + o) = make_short2(a, b);
+    } else {
+      p.pcm[o] = a;
+      p.pcm[o + 1] = b;
+    }
   }
 }
 
