@@ -47,16 +47,19 @@ inline cascade_fn pick_cascade(int src, int dc, bool arb, const int* ms, int* G)
   if (!arb) {
     if (dc == DC_ZSR && src == SRC_CU8) {
       if (is(5, 0, 0, 0)) return cfn<SRC_CU8, DC_ZSR, 16, 5, 0, 0, 0, false>();
+      if (is(5, 10, 0, 0)) return cfn<SRC_CU8, DC_ZSR, 16, 5, 10, 0, 0, false>();
       if (is(3, 5, 0, 0)) return cfn<SRC_CU8, DC_ZSR, 16, 3, 5, 0, 0, false>();
       if (is(3, 3, 3, 3)) return cfn<SRC_CU8, DC_ZSR, 16, 3, 3, 3, 3, false>();
     }
     if (dc == DC_ZSR && src == SRC_CF32) {
       if (is(5, 0, 0, 0)) return cfn<SRC_CF32, DC_ZSR, 16, 5, 0, 0, 0, false>();
+      if (is(5, 10, 0, 0)) return cfn<SRC_CF32, DC_ZSR, 16, 5, 10, 0, 0, false>();
       if (is(3, 5, 0, 0)) return cfn<SRC_CF32, DC_ZSR, 16, 3, 5, 0, 0, false>();
       if (is(3, 3, 3, 3)) return cfn<SRC_CF32, DC_ZSR, 16, 3, 3, 3, 3, false>();
     }
     if (dc == DC_NONE && src == SRC_CF32) {   // stand-alone msresamp_crcf (liquid shim): input is already DC-blocked
       if (is(5, 0, 0, 0)) return cfn<SRC_CF32, DC_NONE, 16, 5, 0, 0, 0, false>();
+      if (is(5, 10, 0, 0)) return cfn<SRC_CF32, DC_NONE, 16, 5, 10, 0, 0, false>();
       if (is(3, 5, 0, 0)) return cfn<SRC_CF32, DC_NONE, 16, 3, 5, 0, 0, false>();
       if (is(3, 3, 3, 3)) return cfn<SRC_CF32, DC_NONE, 16, 3, 3, 3, 3, false>();
     }
@@ -66,6 +69,7 @@ inline cascade_fn pick_cascade(int src, int dc, bool arb, const int* ms, int* G)
     }
   } else {
     if (dc == DC_NONE && src == SRC_RING && is(10, 0, 0, 0)) { *G = 8; return cfn<SRC_RING, DC_NONE, 8, 10, 0, 0, 0, true>(); }
+    if (dc == DC_NONE && src == SRC_RING && is(0, 0, 0, 0)) { *G = 8; return cfn<SRC_RING, DC_NONE, 8, 0, 0, 0, 0, true>(); }
     if (dc == DC_SCAN && src == SRC_CU8 && is(0, 0, 0, 0)) return cfn<SRC_CU8, DC_SCAN, 16, 0, 0, 0, 0, true>();
     if (dc == DC_SCAN && src == SRC_CF32 && is(0, 0, 0, 0)) return cfn<SRC_CF32, DC_SCAN, 16, 0, 0, 0, 0, true>();
     if (dc == DC_NONE && src == SRC_CF32 && is(0, 0, 0, 0)) return cfn<SRC_CF32, DC_NONE, 16, 0, 0, 0, 0, true>();
@@ -142,7 +146,12 @@ struct Frontend {
     for (int g = (int)plan.stages - 1; g >= 0; g--) order.push_back((int)plan.m[g]);
     std::vector<std::vector<int>> groups;   // pre-launch groups, then the arb launch
     std::vector<int> last;
-    if (!order.empty()) { last.push_back(order.back()); order.pop_back(); }
+    // Two-stage plans whose resampler phase is not periodic (1.024 Msps -> 200 kHz: [5, 10], step 21 474 836): both
+    // half-bands run in the first launch and the last one is the resampler alone -- the ring between them then sits at
+    // the lowest rate (half the traffic) and the per-lane filter-bank gathers no longer share a kernel with the 58-register
+    // m = 10 window.  Otherwise the last half-band goes with the resampler (tiled kernel when the phase has period 2).
+    const bool split_arb = order.size() == 2 && order[0] == 5 && order[1] == 10 && plan.step != (3u << 23);
+    if (!order.empty() && !split_arb) { last.push_back(order.back()); order.pop_back(); }
     for (size_t i = 0; i < order.size(); i += 4) groups.emplace_back(order.begin() + i, order.begin() + std::min(order.size(), i + 4));
     groups.push_back(last);   // may be empty (rate >= 0.5)
     levels.resize(groups.size());
