@@ -107,7 +107,7 @@ __device__ __forceinline__ void twiddle_powers(float2* v, float2 w) {
   for (int k = 1; k < 16; k++) v[af_dig(k)] = cmul(v[af_dig(k)], pw[k]);
 }
 
-static __global__ void __launch_bounds__(AF_T, 3) audio_fft_kernel(AudioFftParams p) {
+static __global__ void __launch_bounds__(AF_T, 4) audio_fft_kernel(AudioFftParams p) {
   __shared__ float2 sm[AF_SMEM];
   const int t = threadIdx.x;
   const int pair = blockIdx.x / p.tiles;
