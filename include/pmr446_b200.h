@@ -64,6 +64,8 @@ typedef struct {
   const float *lp_taps;    /* audio low-pass FIR, NULL = the reference's 103 taps (:106-119) */
   unsigned lp_len;
   float deemph_b0, deemph_b1, deemph_a1; /* :461-463 */
+  int deemph_fir;          /* APP_FIR_DEEMPH build of the reference: the 101-tap FIR de-emphasis (:122-135, :458, :896)
+                              instead of the one-pole filter; served by the fast-convolution audio kernel only */
 } pmr446_config;
 
 /* Per-call outputs.  Any pointer may be NULL.  For *_execute() these are HOST pointers, for

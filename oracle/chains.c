@@ -53,6 +53,7 @@ struct oracle_pmr_s {
   wdelayf *ctcss_lp_delay;  /* [M] */
   firfilt_rrrf *audio_filt; /* [M] */
   iirfilt_rrrf *deemph;     /* [M] */
+  firfilt_rrrf *deemph_fir; /* [M], APP_FIR_DEEMPH variant */
   cbuffercf resamp_buf;
   asgramcf asgram;
   cf *buffp, *resamp_tmp, *chan_tmp;
@@ -99,6 +100,9 @@ oracle_pmr *oracle_pmr_create(const oracle_pmr_cfg *cfg) {
   o->ctcss_lp_delay = (wdelayf *)calloc(M, sizeof(wdelayf));
   o->audio_filt = (firfilt_rrrf *)calloc(M, sizeof(firfilt_rrrf));
   o->deemph = (iirfilt_rrrf *)calloc(M, sizeof(iirfilt_rrrf));
+  o->deemph_fir = (firfilt_rrrf *)calloc(M, sizeof(firfilt_rrrf));
+  float de[PMR446_FIR_DEEMPH_TAPS_LEN];
+  pmr446_fir_deemph_taps_fill(de);
   for (unsigned i = 0; i < M; i++) {
     o->fm_demod[i] = freqdem_create(cfg->kf);
     o->ctcss_filt[i] = firfilt_rrrf_create(hp, PMR446_HP_AUDIO_TAPS_LEN);
@@ -106,6 +110,7 @@ oracle_pmr *oracle_pmr_create(const oracle_pmr_cfg *cfg) {
     o->audio_filt[i] = firfilt_rrrf_create(lp, PMR446_LP_AUDIO_TAPS_LEN);
     o->deemph[i] = iirfilt_rrrf_create((float[]){PMR446_DEEMPH_B0, PMR446_DEEMPH_B1}, 2,
                                        (float[]){PMR446_DEEMPH_A0, PMR446_DEEMPH_A1}, 2);
+    o->deemph_fir[i] = firfilt_rrrf_create(de, PMR446_FIR_DEEMPH_TAPS_LEN); /* :458 */
   }
   /* buffer sizes, :730-732 */
   o->res_size = (unsigned)ceilf(1 + 2 * cfg->chunk * (fs_res / (float)cfg->fs_in));
@@ -131,7 +136,9 @@ void oracle_pmr_destroy(oracle_pmr *o) {
     wdelayf_destroy(o->ctcss_lp_delay[i]);
     firfilt_rrrf_destroy(o->audio_filt[i]);
     iirfilt_rrrf_destroy(o->deemph[i]);
+    firfilt_rrrf_destroy(o->deemph_fir[i]);
   }
+  free(o->deemph_fir);
   free(o->fm_demod); free(o->ctcss_filt); free(o->ctcss_lp_delay); free(o->audio_filt); free(o->deemph);
   if (o->asgram) asgramcf_destroy(o->asgram);
   cbuffercf_destroy(o->resamp_buf);
@@ -195,7 +202,8 @@ int oracle_pmr_execute(oracle_pmr *o, const void *iq, unsigned n, const oracle_p
       t2[k] *= o->cfg.audio_gain;
     }
     if (out->lpcomp) memcpy(out->lpcomp + (size_t)i * out->ld, t1, (size_t)ns * sizeof(float));
-    iirfilt_rrrf_execute_block(o->deemph[i], t2, ns, t2);
+    if (o->cfg.deemph_fir) firfilt_rrrf_execute_block(o->deemph_fir[i], t2, ns, t2); /* :896 */
+    else iirfilt_rrrf_execute_block(o->deemph[i], t2, ns, t2);                       /* :898 */
     if (o->cfg.lowpass) firfilt_rrrf_execute_block(o->audio_filt[i], t2, ns, t2);
     if (out->audio) memcpy(out->audio + (size_t)i * out->ld, t2, (size_t)ns * sizeof(float));
     if (out->pcm)

@@ -32,6 +32,7 @@ typedef struct {
   unsigned chunk;          /* max samples per execute()                                 */
   int active_only;         /* -1: demodulate all channels; k: only channel k            */
   int channelize_only;     /* stop after the channelizer (timing of the front half)     */
+  int deemph_fir;          /* APP_FIR_DEEMPH build: 101-tap FIR de-emphasis (:122-135, :458) */
 } oracle_pmr_cfg;
 
 /* per-chunk outputs; any pointer may be NULL.  Channel-major arrays use row stride ld. */

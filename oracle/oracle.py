@@ -20,7 +20,7 @@ class PmrCfg(C.Structure):
     _fields_ = [("fs_in", C.c_uint), ("in_fmt", C.c_int), ("num_channels", C.c_uint), ("channel_width", C.c_uint),
                 ("pfb_m", C.c_uint), ("pfb_as", C.c_float), ("resamp_as", C.c_float), ("dc_alpha", C.c_float),
                 ("kf", C.c_float), ("audio_gain", C.c_float), ("lowpass", C.c_int), ("waterfall", C.c_uint),
-                ("chunk", C.c_uint), ("active_only", C.c_int), ("channelize_only", C.c_int)]
+                ("chunk", C.c_uint), ("active_only", C.c_int), ("channelize_only", C.c_int), ("deemph_fir", C.c_int)]
 
 
 class PmrOut(C.Structure):

@@ -22,7 +22,7 @@ class Config(C.Structure):
                 ("resamp_as", C.c_float), ("dc_alpha", C.c_float), ("kf", C.c_float), ("audio_gain", C.c_float),
                 ("lowpass", C.c_int), ("waterfall", C.c_uint), ("max_chunk", C.c_uint),
                 ("hp_taps", C.c_void_p), ("hp_len", C.c_uint), ("lp_taps", C.c_void_p), ("lp_len", C.c_uint),
-                ("deemph_b0", C.c_float), ("deemph_b1", C.c_float), ("deemph_a1", C.c_float)]
+                ("deemph_b0", C.c_float), ("deemph_b1", C.c_float), ("deemph_a1", C.c_float), ("deemph_fir", C.c_int)]
 
 
 class Outputs(C.Structure):

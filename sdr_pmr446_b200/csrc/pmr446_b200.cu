@@ -186,7 +186,7 @@ extern "C" int pmr446_batch_create(const pmr446_config* cfg, pmr446_batch** out)
   }
   // fast-convolution response: hp (x gain) * de-emphasis * optional low-pass, as one impulse response < AF_HALO
   {
-    const unsigned fir_len = hpn + (cfg->lowpass ? lpn - 1 : 0);
+    const unsigned fir_len = hpn + (cfg->lowpass ? lpn - 1 : 0) + (cfg->deemph_fir ? PMR446_FIR_DEEMPH_TAPS_LEN - 1 : 0);
     const double a1 = cfg->deemph_a1;
     if (fir_len + 24 <= (unsigned)AF_HALO && fabs(a1) < 0.1) {
       std::vector<double> h(hpt, hpt + hpn);
@@ -196,6 +196,11 @@ extern "C" int pmr446_batch_create(const pmr446_config* cfg, pmr446_batch** out)
       de[0] = cfg->deemph_b0;
       de[1] = (double)cfg->deemph_b1 - a1 * de[0];
       for (size_t n = 2; n < de.size(); n++) de[n] = -a1 * de[n - 1];
+      if (cfg->deemph_fir) {   // APP_FIR_DEEMPH: the reference's 101-tap table instead of the pole
+        std::vector<float> df(PMR446_FIR_DEEMPH_TAPS_LEN);
+        pmr446_fir_deemph_taps_fill(df.data());
+        de.assign(df.begin(), df.end());
+      }
       auto conv = [](const std::vector<double>& x, const std::vector<double>& y) {
         std::vector<double> z(x.size() + y.size() - 1, 0.0);
         for (size_t i = 0; i < x.size(); i++)
@@ -225,6 +230,10 @@ extern "C" int pmr446_batch_create(const pmr446_config* cfg, pmr446_batch** out)
       cudaMemcpy(b->d_aftw.p, tw.data(), AF_N * sizeof(float2), cudaMemcpyHostToDevice);
       b->fft_audio = true;
     }
+  }
+  if (cfg->deemph_fir && !b->fft_audio) {
+    pmr446_batch_destroy(b);
+    return fail(PMR446_EINVAL, "deemph_fir needs the fast-convolution audio path (filters too long for its tile)");
   }
   if (cfg->waterfall > 0) {
     if ((rc = b->wf.init(S, cfg->waterfall))) { pmr446_batch_destroy(b); return rc; }

@@ -73,6 +73,7 @@ extern "C" int pmr446_receiver_create(const pmr446_rx_config* cfg, pmr446_receiv
   const unsigned long long all = M == 64 ? ~0ull : ((1ull << M) - 1);
   if ((cfg->channel_mask & all) == 0) return fail(PMR446_EINVAL, "channel_mask enables no channel");   // :725
   if (cfg->ctcss_block < 1) return fail(PMR446_EINVAL, "ctcss_block must be positive");
+  if (cfg->chain.deemph_fir) return fail(PMR446_EINVAL, "the receiver runs the direct-form audio chain: deemph_fir is not available");
   pmr446_receiver* r = new pmr446_receiver();
   r->cfg = *cfg;
   int rc = pmr446_batch_create(&cfg->chain, &r->batch);
