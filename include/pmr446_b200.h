@@ -65,7 +65,8 @@ typedef struct {
   unsigned lp_len;
   float deemph_b0, deemph_b1, deemph_a1; /* :461-463 */
   int deemph_fir;          /* APP_FIR_DEEMPH build of the reference: the 101-tap FIR de-emphasis (:122-135, :458, :896)
-                              instead of the one-pole filter; served by the fast-convolution audio kernel only */
+                              instead of the one-pole filter; served by the fast-convolution audio kernel only
+                              (batch API; composite responses up to 1000 taps) */
 } pmr446_config;
 
 /* Per-call outputs.  Any pointer may be NULL.  For *_execute() these are HOST pointers, for

@@ -21,8 +21,8 @@ namespace pmr {
 
 constexpr int AF_N = 4096;
 constexpr int AF_T = 256;
-constexpr int AF_HALO = 512;              // >= length of the composite impulse response - 1
-constexpr int AF_OWN = AF_N - AF_HALO;    // outputs kept per tile
+constexpr int AF_HALO = 512;              // overlap of the standard tile: >= length of the composite impulse response - 1
+constexpr int AF_HALO_LONG = 1024;        // second instantiation for longer responses (FIR de-emphasis + low-pass: 579 taps)
 constexpr int AF_SMEM = 16 * 272;         // float2 elements of the exchange buffer
 
 struct AudioFftParams {
@@ -30,7 +30,7 @@ struct AudioFftParams {
   long long demod_stride, demod_mask;
   int rows;                  // n_streams * num_channels
   int tiles;                 // tiles per row pair
-  long long tile0;           // tile k covers outputs [k AF_OWN, (k + 1) AF_OWN)
+  long long tile0;           // tile k covers outputs [k own, (k + 1) own), own = AF_N - HALO
   long long f0, f1;          // owned samples; samples >= f1 do not exist yet
   const float2* resp;        // [AF_N] response, element k0 * 256 + t = H[(t >> 4) + 16 (t & 15) + 256 k0] / N
   const float2* tw;          // [AF_N] exp(-2 pi i k / N)
@@ -107,14 +107,16 @@ __device__ __forceinline__ void twiddle_powers(float2* v, float2 w) {
   for (int k = 1; k < 16; k++) v[af_dig(k)] = cmul(v[af_dig(k)], pw[k]);
 }
 
+template <int HALO>   // overlap discarded per tile; the tile keeps AF_N - HALO outputs
 static __global__ void __launch_bounds__(AF_T, 4) audio_fft_kernel(AudioFftParams p) {
+  constexpr int AF_OWN = AF_N - HALO;
   __shared__ float2 sm[AF_SMEM];
   const int t = threadIdx.x;
   const int pair = blockIdx.x / p.tiles;
   const long long tile = p.tile0 + blockIdx.x % p.tiles;
   const int row1 = 2 * pair, row2 = 2 * pair + 1;
   const bool has2 = row2 < p.rows;
-  const long long o0 = tile * AF_OWN - AF_HALO;       // absolute index of tile sample 0
+  const long long o0 = tile * AF_OWN - HALO;       // absolute index of tile sample 0
   const float* d1 = p.demod + (long long)row1 * p.demod_stride;
   const float* d2 = p.demod + (long long)(has2 ? row2 : row1) * p.demod_stride;
   // 32-bit window of existing samples, relative to o0
@@ -192,13 +194,13 @@ static __global__ void __launch_bounds__(AF_T, 4) audio_fft_kernel(AudioFftParam
   for (int k2 = 0; k2 < 16; k2++) w[k2] = sm[k2 * 256 + t];
   dft16<true>(w);
 
-  // ---- keep samples AF_HALO.. of the tile that this call owns ----
+  // ---- keep samples HALO.. of the tile that this call owns ----
   const long long own_lo = (tile * AF_OWN > p.f0 ? tile * AF_OWN : p.f0) - o0;
   const long long own_hi = ((tile + 1) * AF_OWN < p.f1 ? (tile + 1) * AF_OWN : p.f1) - o0;
-  const int s_lo = (int)(own_lo < AF_HALO ? AF_HALO : own_lo), s_hi = (int)(own_hi > AF_N ? AF_N : (own_hi < 0 ? 0 : own_hi));
+  const int s_lo = (int)(own_lo < HALO ? HALO : own_lo), s_hi = (int)(own_hi > AF_N ? AF_N : (own_hi < 0 ? 0 : own_hi));
   const long long col0 = o0 - p.f0;   // column of tile sample 0
 #pragma unroll
-  for (int m = AF_HALO / 256; m < 16; m++) {
+  for (int m = HALO / 256; m < 16; m++) {
     const int i = t + 256 * m;
     if (i >= s_lo && i < s_hi) {
       const float2 y = w[af_dig(m)];

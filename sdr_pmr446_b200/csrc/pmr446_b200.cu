@@ -52,6 +52,7 @@ struct pmr446_batch {
   int max_tiles = 0;
   long long last_f0 = 0, last_ns = 0;   // frame range of the last execute call (pmr446_batch_gather_channel)
   DevBuf d_out_rssi, d_out_edge;
+  int fft_halo = AF_HALO;    // overlap of the FFT audio tile (AF_HALO or AF_HALO_LONG)
   bool fft_audio = false;    // audio / pcm by fast convolution (audio_fft_kernel); the direct-form kernel serves lpcomp
   DevBuf d_resp, d_aftw;
   // waterfall
@@ -188,7 +189,8 @@ extern "C" int pmr446_batch_create(const pmr446_config* cfg, pmr446_batch** out)
   {
     const unsigned fir_len = hpn + (cfg->lowpass ? lpn - 1 : 0) + (cfg->deemph_fir ? PMR446_FIR_DEEMPH_TAPS_LEN - 1 : 0);
     const double a1 = cfg->deemph_a1;
-    if (fir_len + 24 <= (unsigned)AF_HALO && fabs(a1) < 0.1) {
+    if (fir_len + 24 <= (unsigned)AF_HALO_LONG && fabs(a1) < 0.1) {
+      b->fft_halo = fir_len + 24 <= (unsigned)AF_HALO ? AF_HALO : AF_HALO_LONG;
       std::vector<double> h(hpt, hpt + hpn);
       for (auto& x : h) x *= (double)cfg->audio_gain;
       // de-emphasis (A.1): y[n] = b0 x[n] + b1 x[n-1] - a1 y[n-1]
@@ -441,8 +443,9 @@ extern "C" int pmr446_batch_execute_device(pmr446_batch* b, const void* iq, long
       fp.demod_stride = b->demod_cap;
       fp.demod_mask = b->demod_cap - 1;
       fp.rows = S * M;
-      fp.tile0 = f0 / AF_OWN;
-      fp.tiles = (int)((f1 + AF_OWN - 1) / AF_OWN - fp.tile0);
+      const long long af_own = AF_N - b->fft_halo;
+      fp.tile0 = f0 / af_own;
+      fp.tiles = (int)((f1 + af_own - 1) / af_own - fp.tile0);
       fp.f0 = f0;
       fp.f1 = f1;
       fp.resp = (const float2*)b->d_resp.p;
@@ -450,7 +453,9 @@ extern "C" int pmr446_batch_execute_device(pmr446_batch* b, const void* iq, long
       fp.audio = out->audio;
       fp.pcm = out->pcm;
       fp.out_ld = out->ld;
-      audio_fft_kernel<<<(unsigned)((long long)((fp.rows + 1) / 2) * fp.tiles), AF_T, 0, st>>>(fp);
+      const unsigned fgrid = (unsigned)((long long)((fp.rows + 1) / 2) * fp.tiles);
+      if (b->fft_halo == AF_HALO) audio_fft_kernel<AF_HALO><<<fgrid, AF_T, 0, st>>>(fp);
+      else audio_fft_kernel<AF_HALO_LONG><<<fgrid, AF_T, 0, st>>>(fp);
       b->launches++;
       b->timer.mark(st, TM_AUDIO);
     }

@@ -289,10 +289,9 @@ def test_selector_taps_rssi_and_edge_samples():
 
 def test_fir_deemphasis_variant():
     """APP_FIR_DEEMPH build of the reference (101-tap FIR de-emphasis, src/sdr_pmr446.c:122-135, :458, :896): same chain with
-    the FIR folded into the fast-convolution response.  With the audio low-pass on top the composite response no longer
-    fits the FFT tile and creation must refuse."""
+    the FIR folded into the fast-convolution response, without and with the audio low-pass."""
     from oracle import oracle as orc
-    from sdr_pmr446_b200 import _lib, chain, synth
+    from sdr_pmr446_b200 import chain, synth
     fs, n = 1024000, 400000
     car = synth.CFG1_CARRIERS
     iq = synth.make_cu8(synth.CaptureSpec(fs=float(fs), carriers=car), n, 481)
@@ -313,5 +312,13 @@ def test_fir_deemphasis_variant():
         d = g["lpcomp"][0, c, sl] - r["lpcomp"][c, sl]
         assert np.sqrt(np.mean(d ** 2)) / np.sqrt(np.mean(r["demod"][c, sl] ** 2)) < REL_RMS_TOL
         assert rel_rms(r["audio"][c, 600:], rp["audio"][c, 600:]) > 0.05     # it really is a different filter
-    with pytest.raises(_lib.Pmr446Error):
-        chain.PmrBatch(n_streams=1, fs_in=fs, in_fmt=1, deemph_fir=1, lowpass=1, max_chunk=100000)
+    # with the audio low-pass on top the composite response has 579 taps: the kernel's 1024-sample overlap variant
+    gpu = chain.PmrBatch(n_streams=1, fs_in=fs, in_fmt=1, audio_gain=1.0, deemph_fir=1, lowpass=1, max_chunk=100000)
+    g = gpu.run(iq[None, :], 100000, want=("pcm",))
+    gpu.close()
+    ref = orc.PmrOracle(fs_in=fs, in_fmt=1, audio_gain=1.0, deemph_fir=1, lowpass=1, chunk=100000)
+    r = ref.run(iq, 100000, want=("pcm",))
+    ref.close()
+    for c in active_channels(car):
+        dp = np.abs(g["pcm"][0, c, 700:].astype(np.int32) - r["pcm"][c, 700:].astype(np.int32))
+        assert dp.max() <= PCM_TOL_LSB, ("pcm lowpass", c, int(dp.max()))
