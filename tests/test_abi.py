@@ -122,3 +122,24 @@ def test_resampled_count_matches_oracle_for_any_length(rate):
         total_out += ny.value
         assert L.pmr446_count_resampled(rate, 60.0, total_in) == total_out
     O.msresamp_crcf_destroy(q)
+
+
+def test_receiver_argument_checks_need_no_device():
+    """pmr446_receiver_create validates its own arguments before touching the GPU (reference: exits when the channel
+    mask is empty, src/sdr_pmr446.c:725; MAX_CHANNELS 64, :18)."""
+    L = _lib.lib()
+    cfg = _lib.RxConfig()
+    L.pmr446_rx_default_config(C.byref(cfg))
+    assert cfg.squelch_level == 18.0 and cfg.ctcss_block == 2441 and cfg.lock_mode == 0 and cfg.chain.num_channels == 16
+    h = C.c_void_p()
+    cfg.channel_mask = 0xFFFF0000            # no enabled channel among the 16
+    assert L.pmr446_receiver_create(C.byref(cfg), C.byref(h)) == _lib.EINVAL and not h.value
+    assert b"channel_mask" in L.pmr446_last_error()
+    L.pmr446_rx_default_config(C.byref(cfg))
+    cfg.chain.num_channels = 80
+    assert L.pmr446_receiver_create(C.byref(cfg), C.byref(h)) == _lib.EINVAL
+    L.pmr446_rx_default_config(C.byref(cfg))
+    cfg.chain.deemph_fir = 1
+    assert L.pmr446_receiver_create(C.byref(cfg), C.byref(h)) == _lib.EINVAL
+    assert L.pmr446_receiver_create(None, C.byref(h)) == _lib.EINVAL
+    assert L.pmr446_receiver_max_ns(None) == 0 and L.pmr446_receiver_destroy(None) == _lib.OK
