@@ -38,6 +38,7 @@ struct pmr446_batch {
   // channelizer
   int M = 16;                // channels
   bool generic = false;      // generic-M kernel instead of the 16-channel register kernel
+  bool generic_tile = false; // ... its register-tiled variant (26 taps per branch, 10 frames of M samples in shared memory)
   DevBuf d_pfb_taps, d_mixed, d_tw;
   std::vector<int> radix;
   unsigned dtheta = 0;
@@ -162,6 +163,9 @@ extern "C" int pmr446_batch_create(const pmr446_config* cfg, pmr446_batch** out)
     const size_t smem = (size_t)M * (3 * sizeof(float2) + CG_FT * sizeof(float));
     if (smem > 200 * 1024) { pmr446_batch_destroy(b); return fail(PMR446_EINVAL, "num_channels too large for the shared-memory FFT"); }
     cudaFuncSetAttribute(channelize_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    b->generic_tile = cfg->pfb_m == 13 && channelize_generic_tile_smem(M) <= 200 * 1024;
+    if (b->generic_tile)
+      cudaFuncSetAttribute(channelize_generic_tile_kernel<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)channelize_generic_tile_smem(M));
   }
 
   b->max_tiles = (int)(b->max_ns / CH_TL + 3);
@@ -384,7 +388,8 @@ extern "C" int pmr446_batch_execute_device(pmr446_batch* b, const void* iq, long
     gp.chan = (float2*)out->chan;
     gp.chan_ld = out->ld;
     const size_t smem = (size_t)M * (3 * sizeof(float2) + CG_FT * sizeof(float));
-    channelize_generic_kernel<<<(unsigned)((long long)S * gp.tiles), 256, smem, st>>>(gp);
+    if (b->generic_tile) channelize_generic_tile_kernel<26><<<(unsigned)((long long)S * gp.tiles), 512, channelize_generic_tile_smem(M), st>>>(gp);
+    else channelize_generic_kernel<<<(unsigned)((long long)S * gp.tiles), 256, smem, st>>>(gp);
     b->launches += 2;
     b->timer.mark(st, TM_CHANNELIZE);
   } else if (ns > 0) {
