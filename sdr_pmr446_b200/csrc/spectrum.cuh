@@ -128,22 +128,37 @@ static __global__ void __launch_bounds__(1024) wf_accumulate_kernel(WfParams p) 
   for (int t = 1 + part; t <= p.n_transforms; t += p.parts) {
     __syncthreads();
     const long long first = (long long)t * p.hop - p.W;  // chunk-local index of window sample 0
-    for (int i = threadIdx.x; i < p.nfft; i += blockDim.x) {
-      float2 v = make_float2(0.0f, 0.0f);
-      if (i < p.W) {
+    // nfft = 4 W with a leading radix-4 stage: its inputs 1..3 are the zero padding, so the stage is the load itself
+    const bool lead4 = p.radix[0] == 4 && p.nfft == 4 * p.W;
+    if (lead4) {
+      for (int i = threadIdx.x; i < p.W; i += blockDim.x) {
         const long long li = first + i;
+        float2 v = make_float2(0.0f, 0.0f);
         if (li >= 0) {
           const float2 x = res[(p.r0 + li) & p.res_mask];
           const float w = p.window[i];
           v = make_float2(x.x * w, x.y * w);
         }
+        b[4 * i] = v; b[4 * i + 1] = v; b[4 * i + 2] = v; b[4 * i + 3] = v;
       }
-      a[i] = v;
+    } else {
+      for (int i = threadIdx.x; i < p.nfft; i += blockDim.x) {
+        float2 v = make_float2(0.0f, 0.0f);
+        if (i < p.W) {
+          const long long li = first + i;
+          if (li >= 0) {
+            const float2 x = res[(p.r0 + li) & p.res_mask];
+            const float w = p.window[i];
+            v = make_float2(x.x * w, x.y * w);
+          }
+        }
+        a[i] = v;
+      }
     }
     __syncthreads();
-    float2 *x = a, *y = b;
-    int Ns = 1;
-    for (int st = 0; st < p.n_stages; st++) {
+    float2 *x = lead4 ? b : a, *y = lead4 ? a : b;
+    int Ns = lead4 ? 4 : 1;
+    for (int st = lead4 ? 1 : 0; st < p.n_stages; st++) {
       const int R = p.radix[st];
       if (R == 4) wf_stage<4>(x, y, p.twiddle, p.nfft, Ns);
       else if (R == 2) wf_stage<2>(x, y, p.twiddle, p.nfft, Ns);
