@@ -57,6 +57,7 @@ extern "C" int dsd446_batch_create(const dsd446_config* cfg, dsd446_batch** out)
   *out = nullptr;
   if (cfg->n_streams < 1 || cfg->max_chunk < 1 || cfg->fs_in == 0 || cfg->fs_sig == 0) return fail(PMR446_EINVAL, "bad configuration");
   if (int rc = select_device(cfg->device)) return rc;
+  cudaGetLastError();   // clean slate for the check at the end
   dsd446_batch* b = new dsd446_batch();
   b->cfg = *cfg;
   b->S = cfg->n_streams;
@@ -83,7 +84,10 @@ extern "C" int dsd446_batch_create(const dsd446_config* cfg, dsd446_batch** out)
   }
   cudaMemcpy(b->d_pfb_up.p, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice);
   CUDA_TRY(cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking));
-  CUDA_TRY(cudaDeviceSynchronize());
+  if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+    dsd446_batch_destroy(b);
+    return fail(PMR446_ECUDA, "CUDA error while setting up the dsd batch");
+  }
   *out = b;
   return PMR446_OK;
 }

@@ -111,6 +111,7 @@ extern "C" int pmr446_batch_create(const pmr446_config* cfg, pmr446_batch** out)
   if (cfg->num_channels < 2 || cfg->num_channels > 4096 || cfg->pfb_m < 1 || cfg->pfb_m > 32)
     return fail(PMR446_EINVAL, "num_channels must be in [2, 4096] and pfb_m in [1, 32]");
   if (int rc = select_device(cfg->device)) return rc;
+  cudaGetLastError();   // start from a clean slate: the check at the end only sees errors raised in here
   pmr446_batch* b = new pmr446_batch();
   b->cfg = *cfg;
   b->S = cfg->n_streams;
@@ -253,7 +254,11 @@ extern "C" int pmr446_batch_create(const pmr446_config* cfg, pmr446_batch** out)
     CUDA_TRY(cudaEventCreateWithFlags(&b->ev_copied[i], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&b->ev_free[i], cudaEventDisableTiming));
   }
-  CUDA_TRY(cudaDeviceSynchronize());
+  // every table upload and attribute call above is synchronous: one check for all of them
+  if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+    pmr446_batch_destroy(b);
+    return fail(PMR446_ECUDA, "CUDA error while setting up the batch");
+  }
   *out = b;
   return PMR446_OK;
 }

@@ -78,6 +78,7 @@ extern "C" int pmr446_receiver_create(const pmr446_rx_config* cfg, pmr446_receiv
   r->cfg = *cfg;
   int rc = pmr446_batch_create(&cfg->chain, &r->batch);
   if (rc) { delete r; return rc; }
+  cudaGetLastError();
   cudaGetDevice(&r->device);
   const int S = r->S = cfg->chain.n_streams;
   r->M = (int)M;
@@ -111,7 +112,10 @@ extern "C" int pmr446_receiver_create(const pmr446_rx_config* cfg, pmr446_receiv
   cudaMemcpy(r->d_freqs.p, pmr446_ctcss_freqs, sizeof pmr446_ctcss_freqs, cudaMemcpyHostToDevice);
   cudaFuncSetAttribute(audio_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   CUDA_TRY(cudaStreamCreateWithFlags(&r->own_stream, cudaStreamNonBlocking));
-  CUDA_TRY(cudaDeviceSynchronize());
+  if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+    pmr446_receiver_destroy(r);
+    return fail(PMR446_ECUDA, "CUDA error while setting up the receiver");
+  }
   *out = r;
   return PMR446_OK;
 }
