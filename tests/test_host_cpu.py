@@ -83,3 +83,12 @@ def test_python_transcription_of_loop_equals_chain_driver():
     o.close()
     assert np.array_equal(a["res"], r["res"]) and np.array_equal(a["chan"], r["chan"])
     assert np.array_equal(a["audio"], r["audio"][6])
+
+
+def test_public_headers_are_plain_c_and_cxx():
+    """The drop-in boundary is a C ABI: both public headers must compile stand-alone as C99 and as C++."""
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    for hdr in ("pmr446_b200.h", "pmr446_liquid_shim.h"):
+        for lang, std in (("c", "-std=c99"), ("c++", "-std=c++11")):
+            subprocess.check_call(["gcc", "-x", lang, std, "-Wall", "-Werror", "-pedantic", "-fsyntax-only", os.path.join(inc, hdr)])
