@@ -182,7 +182,7 @@ static __global__ void __launch_bounds__(1024) wf_accumulate_kernel(WfParams p) 
 // the warp, __syncwarp between stages, |X|^2 accumulated in registers: bin lane + 32 m), the twiddle table sits in
 // shared memory, and because nfft = 4 W with a leading radix-4 stage whose inputs 1..3 are the zero padding, that stage
 // is the load itself (each windowed sample is written to its four outputs).
-constexpr int WFW_WARPS = 8;   // at most; the launch uses as many as fit in 48 KB of shared memory (no opt-in needed)
+constexpr int WFW_WARPS = 8;   // at most; the launch uses as many as fit in 96 KB of shared memory
 
 template <int R>
 __device__ __forceinline__ void wf_stage_warp(const float2* __restrict__ x, float2* __restrict__ y, const float2* __restrict__ tw, int N, int Ns,
@@ -419,7 +419,7 @@ struct Waterfall {
     // enough (stream, part) blocks to fill the GPU: one block needs nfft * 20 bytes of shared memory (block-per-transform
     // kernel) or nfft * 8 * (1 + 2 * 8 warps) bytes (warp-per-transform kernel, nfft <= 1024)
     warp_kernel = nfft <= 1024;
-    wf_warps = std::max(1, std::min(WFW_WARPS, (int)((48 * 1024 / (nfft * sizeof(float2)) - 1) / 2)));
+    wf_warps = std::max(1, std::min(WFW_WARPS, (int)((96 * 1024 / (nfft * sizeof(float2)) - 1) / 2)));
     {
       const size_t per_block = warp_kernel ? (size_t)nfft * sizeof(float2) * (1 + 2 * wf_warps) : (size_t)nfft * (2 * sizeof(float2) + sizeof(float));
       const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / per_block));
@@ -432,6 +432,11 @@ struct Waterfall {
     CUDA_TRY(cudaMemcpy(d_window.p, w.data(), W * sizeof(float), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d_twiddle.p, tw.data(), nfft * sizeof(float2), cudaMemcpyHostToDevice));
     smem = warp_kernel ? (size_t)nfft * sizeof(float2) * (1 + 2 * wf_warps) : (size_t)nfft * (2 * sizeof(float2) + sizeof(float));
+    if (warp_kernel && smem > 48 * 1024) {
+      CUDA_TRY(cudaFuncSetAttribute(wf_accumulate_warp_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_TRY(cudaFuncSetAttribute(wf_accumulate_warp_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_TRY(cudaFuncSetAttribute(wf_accumulate_warp_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     if (!warp_kernel) CUDA_TRY(cudaFuncSetAttribute(wf_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return 0;
   }
