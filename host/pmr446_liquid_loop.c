@@ -148,7 +148,11 @@ int main(int argc, char **argv) {
         }
         iirfilt_rrrf_execute_block(chain.deemph, tmp_buf2, (unsigned)ns, tmp_buf2);
         if (lowpass) firfilt_rrrf_execute_block(chain.audio_filt, tmp_buf2, (unsigned)ns, tmp_buf2);
-        for (size_t k = 0; k < ns; k++) pcm[k] = (int16_t)(int32_t)(tmp_buf2[k] * (float)INT16_MAX);   /* src/dsd_in.c:172-175 */
+        for (size_t k = 0; k < ns; k++) {   /* src/dsd_in.c:172-175, saturated like the device clips RtAudio's float audio */
+          float y = tmp_buf2[k] * (float)INT16_MAX;
+          y = y < -32768.0f ? -32768.0f : (y > 32767.0f ? 32767.0f : y);
+          pcm[k] = (int16_t)(int32_t)y;
+        }
         CHECK(fwrite(pcm, 2, ns, fo) == ns);   /* was cbufferf_write to RtAudio, :903-906 */
         total += ns;
       }

@@ -57,7 +57,7 @@ typedef struct {
   float kf;                /* freqdem_create, :440 (0.5) */
   float audio_gain;        /* SDR_DEFAULT_AUDIO_GAIN, :33 (4.0) */
   int lowpass;             /* -l: apply the 103-tap audio low-pass, :900-902 */
-  unsigned waterfall;      /* -w W: asgram width, 0 = off, :473-477 */
+  unsigned waterfall;      /* -w W: asgram width, 0 = off, :473-477; any W in [2, 2048] (nfft = 4 W, any factorisation) */
   unsigned max_chunk;      /* largest n per execute call (SDR_INPUT_CHUNK, :30) */
   const float *hp_taps;    /* CTCSS-removal FIR, NULL = the reference's 377 taps (:56-104) */
   unsigned hp_len;
@@ -79,7 +79,7 @@ typedef struct {
   float *demod;            /* [n_streams][M][ld] discriminator output (tmp_buf1 after :881) */
   float *lpcomp;           /* [n_streams][M][ld] delayed - high-passed (tmp_buf1 after :889) */
   float *audio;            /* [n_streams][M][ld] float audio (tmp_buf2 after :898/:901) */
-  int16_t *pcm;            /* [n_streams][M][ld] (int16_t)(audio * 32767) */
+  int16_t *pcm;            /* [n_streams][M][ld] (int16_t)(audio * 32767), saturated at full scale */
   long long ld;            /* samples per channel row (SDR_CHANNEL_BUF_SIZE, :37) */
   char *ascii;             /* [n_streams][W] waterfall row (asgramcf_execute, :912) */
   float *peak;             /* [n_streams][2] peak value (dB) and frequency */

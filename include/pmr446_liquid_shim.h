@@ -127,7 +127,10 @@ int cbufferf_read(cbufferf q, unsigned int n, float **v, unsigned int *nr);
 int cbufferf_release(cbufferf q, unsigned int n);
 int cbufferf_destroy(cbufferf q);
 
-/* asgramcf: src/sdr_pmr446.c:474-476,911-912,486 */
+/* asgramcf: src/sdr_pmr446.c:474-476,911-912,486.
+ * Limits of this implementation (liquid has none): nfft (the terminal width) in [2, 2048]; at most 2^18 samples may be
+ * written between two asgramcf_execute() calls (asgramcf_write returns LIQUID_EIRANGE beyond that; the reference writes
+ * <= 39 064 per execute, :911-912).  asgramcf_create() returns NULL outside the width range; pmr446_last_error() says why. */
 typedef struct asgramcf_s *asgramcf;
 asgramcf asgramcf_create(unsigned int nfft);
 int asgramcf_set_scale(asgramcf q, float ref, float div);

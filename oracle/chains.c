@@ -13,7 +13,8 @@
  *     cfg.active_only >= 0 gives the reference-faithful single-channel cost for CPU timing;
  *   - the squelch state machine, CTCSS detector, RtAudio and terminal output are out of scope;
  *   - sample rate, channel count and chunk size are configuration instead of #defines;
- *   - s16 output for the PMR chain uses dsd_in's conversion (src/dsd_in.c:172-175).
+ *   - s16 output for the PMR chain uses dsd_in's conversion (src/dsd_in.c:172-175), saturated at +-full scale (the
+ *     reference's PMR audio is float32 clipped by the audio device, never a wrapping cast).
  */
 #include "chains.h"
 
@@ -25,7 +26,12 @@
 
 typedef float _Complex cf;
 
-static inline int16_t to_s16(float v) { return (int16_t)(int32_t)(v * (float)INT16_MAX); }
+static inline int16_t to_s16(float v) { return (int16_t)(int32_t)(v * (float)INT16_MAX); }   /* dsd_in: plain C cast */
+static inline int16_t to_s16_sat(float v) {
+  float y = v * (float)INT16_MAX;
+  y = y < -32768.0f ? -32768.0f : (y > 32767.0f ? 32767.0f : y);
+  return (int16_t)(int32_t)y;
+}
 
 static void convert_in(int fmt, const void *iq, unsigned n, cf *out) {
   if (fmt == ORACLE_FMT_CF32) {
@@ -207,7 +213,7 @@ int oracle_pmr_execute(oracle_pmr *o, const void *iq, unsigned n, const oracle_p
     if (o->cfg.lowpass) firfilt_rrrf_execute_block(o->audio_filt[i], t2, ns, t2);
     if (out->audio) memcpy(out->audio + (size_t)i * out->ld, t2, (size_t)ns * sizeof(float));
     if (out->pcm)
-      for (unsigned k = 0; k < ns; k++) out->pcm[(size_t)i * out->ld + k] = to_s16(t2[k]);
+      for (unsigned k = 0; k < ns; k++) out->pcm[(size_t)i * out->ld + k] = to_s16_sat(t2[k]);
   }
 
   /* :910-913 -- note the waterfall sees the UN-mixed resampler output (local array, :911) */

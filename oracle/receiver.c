@@ -227,7 +227,11 @@ int oracle_rx_execute(oracle_rx *o, const void *iq, unsigned n, const oracle_rx_
     if (o->cfg.chain.lowpass) firfilt_rrrf_execute_block(o->audio_filt, t2, ns, t2);
     if (out->audio) memcpy(out->audio, t2, (size_t)ns * sizeof(float));
     if (out->pcm)
-      for (unsigned k = 0; k < ns; k++) out->pcm[k] = (int16_t)(int32_t)(t2[k] * (float)INT16_MAX);
+      for (unsigned k = 0; k < ns; k++) {
+        float y = t2[k] * (float)INT16_MAX;   /* saturating, see chains.c to_s16_sat */
+        y = y < -32768.0f ? -32768.0f : (y > 32767.0f ? 32767.0f : y);
+        out->pcm[k] = (int16_t)(int32_t)y;
+      }
     n_audio = ns;
   }
   if (out->ctcss_power) memcpy(out->ctcss_power, o->tones.power, sizeof o->tones.power);

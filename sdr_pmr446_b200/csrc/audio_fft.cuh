@@ -19,6 +19,14 @@
 
 namespace pmr {
 
+// PMR audio float -> s16: (int16_t)(v * 32767) like src/dsd_in.c:172-175, but SATURATING.  The reference's PMR path hands
+// float audio to RtAudio, where the device clips; with the default audio_gain = 4 a full-deviation signal reaches +-1.6,
+// and a wrapping cast would flip its sign.  (dsd_in's own cast, dsd.cuh, stays the plain C cast for bit parity.)
+#ifndef PMR_PCM_SAT_DEFINED
+#define PMR_PCM_SAT_DEFINED
+__device__ __forceinline__ short pcm_sat(float v) { return (short)__float2int_rz(fminf(fmaxf(v * 32767.0f, -32768.0f), 32767.0f)); }
+#endif
+
 constexpr int AF_N = 4096;
 constexpr int AF_T = 256;
 constexpr int AF_HALO = 512;              // overlap of the standard tile: >= length of the composite impulse response - 1
@@ -210,8 +218,8 @@ static __global__ void __launch_bounds__(AF_T, 4) audio_fft_kernel(AudioFftParam
         if (has2) p.audio[(long long)row2 * p.out_ld + col] = y.y;
       }
       if (p.pcm) {
-        p.pcm[(long long)row1 * p.out_ld + col] = (short)__float2int_rz(y.x * 32767.0f);
-        if (has2) p.pcm[(long long)row2 * p.out_ld + col] = (short)__float2int_rz(y.y * 32767.0f);
+        p.pcm[(long long)row1 * p.out_ld + col] = pcm_sat(y.x);
+        if (has2) p.pcm[(long long)row2 * p.out_ld + col] = pcm_sat(y.y);
       }
     }
   }

@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "audio_fft.cuh"   // pcm_sat
+
 namespace pmr {
 
 // One block = one (stream, channel) row x one time tile.  Thread t owns 16 consecutive output
@@ -208,7 +210,7 @@ static __global__ void __launch_bounds__(AU_THREADS) audio_kernel(AudioParams p)
   for (int i = s_lo + t; i < s_hi; i += AU_THREADS) {
     const float v = xs[padidx(i)];
     if (arow) arow[i - f0r] = v;
-    if (prow) prow[i - f0r] = (short)__float2int_rz(v * 32767.0f);
+    if (prow) prow[i - f0r] = pcm_sat(v);
   }
 }
 

@@ -1,4 +1,4 @@
-// Generic-M analysis channelizer (any channel count with prime factors <= 61, any prototype
+// Generic-M analysis channelizer (any channel count <= 4096 -- large prime factors run an O(p) per output butterfly --, any prototype
 // semi-length): the wideband path of BASELINE config 4 (1600 channels of 12.5 kHz from a 20 Msps
 // capture).  Same arithmetic as channelize16_kernel (replacing
 // /root/reference/src/sdr_pmr446.c:804-823 and :881 for every channel) with M as a parameter:
@@ -91,7 +91,7 @@ static __global__ void __launch_bounds__(256) channelize_generic_kernel(ChanGenP
       else if (R == 2) wf_stage<2>(xa, xb, p.twiddle, M, Ns);
       else if (R == 3) wf_stage<3>(xa, xb, p.twiddle, M, Ns);
       else if (R == 5) wf_stage<5>(xa, xb, p.twiddle, M, Ns);
-      else wf_stage_generic(R, xa, xb, p.twiddle, M, Ns);
+      else wf_stage_generic(R, xa, xb, p.twiddle, M, Ns, threadIdx.x, blockDim.x);
       Ns *= R;
       float2* tmp = xa; xa = xb; xb = tmp;
       __syncthreads();
@@ -176,7 +176,7 @@ static __global__ void __launch_bounds__(512) channelize_generic_tile_kernel(Cha
       else if (R == 2) wf_stage<2>(xa, xb, p.twiddle, M, Ns);
       else if (R == 3) wf_stage<3>(xa, xb, p.twiddle, M, Ns);
       else if (R == 5) wf_stage<5>(xa, xb, p.twiddle, M, Ns);
-      else wf_stage_generic(R, xa, xb, p.twiddle, M, Ns);
+      else wf_stage_generic(R, xa, xb, p.twiddle, M, Ns, threadIdx.x, blockDim.x);
       Ns *= R;
       float2* tmp = xa; xa = xb; xb = tmp;
       __syncthreads();

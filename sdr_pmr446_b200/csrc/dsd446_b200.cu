@@ -99,10 +99,11 @@ extern "C" int dsd446_batch_reset(dsd446_batch* b) {
   if (!b) return fail(PMR446_EINVAL, "null handle");
   cudaSetDevice(b->device);
   cudaDeviceSynchronize();
-  b->fe.reset();
+  if (int rc = b->fe.reset()) return rc;
   b->n_z = 0;
-  cudaMemset(b->d_fm.p, 0, b->d_fm.bytes);
-  cudaMemset(b->d_z.p, 0, b->d_z.bytes);
+  CUDA_TRY(cudaMemset(b->d_fm.p, 0, b->d_fm.bytes));
+  CUDA_TRY(cudaMemset(b->d_z.p, 0, b->d_z.bytes));
+  CUDA_TRY(cudaDeviceSynchronize());   // see pmr446_batch_reset
   return PMR446_OK;
 }
 
@@ -115,13 +116,17 @@ extern "C" int dsd446_batch_execute_device(dsd446_batch* b, const void* iq, long
   const int S = b->S;
   int launches = 0;
   const long long r0 = b->fe.n_out;
+  {  // validate against the closed-form counts BEFORE any state advances: a failed call leaves the handle untouched
+    const long long r1p = b->fe.outputs_after(b->fe.n_in + (long long)n);
+    const long long nzp = 2 * ((long long)design::arb_outputs_after((uint64_t)r1p, b->up.step) - b->n_z);
+    if ((out->res || out->fm) && r1p - r0 > out->res_ld) return fail(PMR446_ERANGE, "res_ld too small");
+    if ((out->audio || out->pcm) && nzp > out->out_ld) return fail(PMR446_ERANGE, "out_ld too small");
+  }
   int rc = b->fe.execute(iq, iq_stride, n, st, &launches);   // src/dsd_in.c:167-168
   if (rc) return rc;
   const long long r1 = b->fe.n_out, ny = r1 - r0;
   const long long k0 = b->n_z, k1 = (long long)design::arb_outputs_after((uint64_t)r1, b->up.step);
   const long long nz = 2 * (k1 - k0);
-  if ((out->res || out->fm) && ny > out->res_ld) return fail(PMR446_ERANGE, "res_ld too small");
-  if ((out->audio || out->pcm) && nz > out->out_ld) return fail(PMR446_ERANGE, "out_ld too small");
   if (ny > 0) {
     dim3 g((unsigned)((ny + 255) / 256), S);
     dsd_freqdem_kernel<<<g, 256, 0, st>>>((const float2*)b->fe.out.p, b->fe.out_cap, b->fe.out_cap - 1, (float*)b->d_fm.p, b->fm_cap,
@@ -174,20 +179,26 @@ extern "C" int dsd446_batch_execute(dsd446_batch* b, const void* iq, long long i
   dsd446_outputs d = *out;
   d.res_ld = b->max_res;
   d.out_ld = b->max_out;
+  int stage_rc = 0;
   auto stage = [&](const void* host, DevBuf& buf, size_t bytes) -> void* {
     if (!host) return nullptr;
-    if (buf.ensure(bytes)) return nullptr;
+    if (int e = buf.ensure(bytes)) { stage_rc = e; return nullptr; }
     return buf.p;
   };
   d.res = (float*)stage(out->res, b->d_res, (size_t)S * d.res_ld * 8);
   d.fm = (float*)stage(out->fm, b->d_fmout, (size_t)S * d.res_ld * 4);
   d.audio = (float*)stage(out->audio, b->d_audio, (size_t)S * d.out_ld * 4);
   d.pcm = (int16_t*)stage(out->pcm, b->d_pcm, (size_t)S * d.out_ld * 2);
+  if (stage_rc) return stage_rc;
+  {  // the caller's leading dimensions, before the state advances
+    const long long r1p = b->fe.outputs_after(b->fe.n_in + (long long)n);
+    const long long nzp = 2 * ((long long)design::arb_outputs_after((uint64_t)r1p, b->up.step) - b->n_z);
+    if ((out->res || out->fm) && r1p - b->fe.n_out > out->res_ld) return fail(PMR446_ERANGE, "res_ld too small");
+    if ((out->audio || out->pcm) && nzp > out->out_ld) return fail(PMR446_ERANGE, "out_ld too small");
+  }
   unsigned ny = 0, nz = 0;
   rc = dsd446_batch_execute_device(b, b->d_in.p, in_row, n, &d, &ny, &nz, st);
   if (rc) return rc;
-  if ((out->res || out->fm) && ny > out->res_ld) return fail(PMR446_ERANGE, "res_ld too small");
-  if ((out->audio || out->pcm) && nz > out->out_ld) return fail(PMR446_ERANGE, "out_ld too small");
   auto back = [&](void* host, const void* dev, long long hld, long long dld, size_t elt, long long cols) {
     if (host && cols > 0) cudaMemcpy2DAsync(host, hld * elt, dev, dld * elt, cols * elt, S, cudaMemcpyDeviceToHost, st);
   };

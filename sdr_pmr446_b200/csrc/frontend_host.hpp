@@ -99,6 +99,11 @@ struct Frontend {
   unsigned max_chunk = 0;
 
   long long max_out_per_chunk() const { return levels.empty() ? 0 : levels.back().max_out; }
+  // resampler outputs that exist once n_total raw samples have been consumed (closed form, A.2/A.5): lets the callers
+  // validate their output buffers BEFORE execute() advances any state
+  long long outputs_after(long long n_total) const {
+    return (long long)design::arb_outputs_after((uint64_t)(n_total >> plan.stages), plan.step);
+  }
 
   // E[k]: response of level 0's stage chain (zero state) to the sequence c^i, i >= 0, in float64
   std::vector<float> zir_table(const Level& L) const {
@@ -261,11 +266,13 @@ struct Frontend {
     hist_base = -(long long)levels[0].halo;
     for (auto& L : levels) L.n_in = L.n_out = 0;
   }
-  void reset() {
+  // zeroes all state; asynchronous on the legacy stream: the caller synchronises the device before returning
+  int reset() {
     reset_counters();
-    for (auto& L : levels) cudaMemset(L.ring.p, 0, L.ring.bytes);
-    for (int i = 0; i < 2; i++) cudaMemset(hist[i].p, 0, hist[i].bytes);
-    cudaMemset(v_lag.p, 0, v_lag.bytes);
+    for (auto& L : levels) CUDA_TRY(cudaMemset(L.ring.p, 0, L.ring.bytes));
+    for (int i = 0; i < 2; i++) CUDA_TRY(cudaMemset(hist[i].p, 0, hist[i].bytes));
+    CUDA_TRY(cudaMemset(v_lag.p, 0, v_lag.bytes));
+    return 0;
   }
 
   // Consumes n raw samples per stream ([n_in, n_in + n)); afterwards n_out is the absolute

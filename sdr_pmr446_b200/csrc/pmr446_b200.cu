@@ -149,8 +149,7 @@ extern "C" int pmr446_batch_create(const pmr446_config* cfg, pmr446_batch** out)
       if (nn % pr == 0) { b->radix.push_back((int)pr); nn /= pr; }
       else pr++;
     }
-    for (int r : b->radix)
-      if (r > 61 || b->radix.size() > 16) { pmr446_batch_destroy(b); return fail(PMR446_EINVAL, "num_channels has a prime factor > 61"); }
+    if (b->radix.size() > 16) { pmr446_batch_destroy(b); return fail(PMR446_EINVAL, "num_channels has more than 16 prime factors"); }
     std::vector<float2> tw(M);
     for (int k = 0; k < M; k++) {
       double a = -2.0 * M_PI * (double)k / (double)M;
@@ -324,8 +323,11 @@ extern "C" int pmr446_batch_reset(pmr446_batch* b) {
   if (!b) return fail(PMR446_EINVAL, "null handle");
   cudaSetDevice(b->device);
   cudaDeviceSynchronize();
-  b->fe.reset();
+  if (int rc = b->fe.reset()) return rc;
   CUDA_TRY(cudaMemset(b->d_demod.p, 0, b->d_demod.bytes));
+  // cudaMemset on device memory is asynchronous to the host and the execute paths run on non-blocking streams, which
+  // do not order against the legacy stream: finish the memsets before any execute call can start
+  CUDA_TRY(cudaDeviceSynchronize());
   return PMR446_OK;
 }
 
@@ -343,6 +345,16 @@ extern "C" int pmr446_batch_execute_device(pmr446_batch* b, const void* iq, long
   const int S = b->S;
   b->launches = 0;
 
+  // ---- validate against the closed-form counts BEFORE any state advances: a failed call leaves the handle untouched ----
+  const int M = b->M;
+  {
+    const long long r0p = b->fe.n_out, r1p = b->fe.outputs_after(b->fe.n_in + (long long)n);
+    const long long nyp = r1p - r0p, nsp = r1p / M - r0p / M;
+    if (out->res && nyp > out->res_ld) return fail(PMR446_ERANGE, "res_ld too small");
+    if ((out->chan || out->demod || out->lpcomp || out->audio || out->pcm) && nsp > out->ld) return fail(PMR446_ERANGE, "ld too small");
+    if ((out->rssi || out->chan_edge) && b->generic) return fail(PMR446_EINVAL, "rssi / chan_edge outputs need the 16-channel kernel");
+    if (!b->generic && (r1p / M + CH_TL - 1) / CH_TL - r0p / M / CH_TL > b->max_tiles) return fail(PMR446_ERANGE, "internal: tile count exceeds allocation");
+  }
   // ---- front end: [r0, r1) new resampler outputs in fe.out ring ------------------------------
   long long r0 = b->fe.n_out, r1 = 0;
   b->timer.mark(st, TM_START);
@@ -350,11 +362,7 @@ extern "C" int pmr446_batch_execute_device(pmr446_batch* b, const void* iq, long
   if (rc) return rc;
   r1 = b->fe.n_out;
   const long long ny = r1 - r0;
-  const int M = b->M;
   const long long f0 = r0 / M, f1 = r1 / M, ns = f1 - f0;  // frames: cbuffer carry of r % M samples (:804)
-  if (out->res && ny > out->res_ld) return fail(PMR446_ERANGE, "res_ld too small");
-  if ((out->chan || out->demod || out->lpcomp || out->audio || out->pcm) && ns > out->ld) return fail(PMR446_ERANGE, "ld too small");
-  if ((out->rssi || out->chan_edge) && b->generic) return fail(PMR446_EINVAL, "rssi / chan_edge outputs need the 16-channel kernel");
   b->last_f0 = f0;
   b->last_ns = ns;
 
@@ -541,9 +549,10 @@ extern "C" int pmr446_batch_execute(pmr446_batch* b, const void* iq, long long i
   const long long ld = b->max_ns, rld = b->max_res;
   d.ld = ld;
   d.res_ld = rld;
+  int stage_rc = 0;   // a failed staging allocation must fail the call, not silently drop the output
   auto stage = [&](const void* host, DevBuf& buf, size_t bytes) -> void* {
     if (!host) return nullptr;
-    if (buf.ensure(bytes)) return nullptr;
+    if (int e = buf.ensure(bytes)) { stage_rc = e; return nullptr; }
     return buf.p;
   };
   d.res = (float*)stage(out->res, b->d_out_res, (size_t)S * rld * 8);
@@ -557,6 +566,12 @@ extern "C" int pmr446_batch_execute(pmr446_batch* b, const void* iq, long long i
   d.psd = (float*)stage(W ? out->psd : nullptr, b->d_out_psd, (size_t)S * 4 * W * 4);
   d.rssi = (float*)stage(out->rssi, b->d_out_rssi, (size_t)S * M * 4);
   d.chan_edge = (float*)stage(out->chan_edge, b->d_out_edge, (size_t)S * M * 2 * 8);
+  if (stage_rc) return stage_rc;
+  {  // the caller's leading dimensions against the closed-form totals, before the first slice advances the state
+    const long long r0p = b->fe.n_out, r1p = b->fe.outputs_after(b->fe.n_in + (long long)n);
+    if (out->res && r1p - r0p > out->res_ld) return fail(PMR446_ERANGE, "res_ld too small");
+    if ((out->chan || out->demod || out->lpcomp || out->audio || out->pcm) && r1p / M - r0p / M > out->ld) return fail(PMR446_ERANGE, "ld too small");
+  }
   unsigned ny_tot = 0, ns_tot = 0;
   int launches = 0;
   unsigned off = 0;

@@ -138,7 +138,9 @@ extern "C" int pmr446_receiver_reset(pmr446_receiver* r) {
   cudaSetDevice(r->device);
   cudaDeviceSynchronize();
   if (int rc = pmr446_batch_reset(r->batch)) return rc;
-  return rx_init_state(r);
+  if (int rc = rx_init_state(r)) return rc;
+  CUDA_TRY(cudaDeviceSynchronize());   // see pmr446_batch_reset
+  return PMR446_OK;
 }
 
 extern "C" int pmr446_receiver_execute_device(pmr446_receiver* r, const void* iq, long long iq_stride, unsigned n, const pmr446_rx_outputs* out,

@@ -95,24 +95,27 @@ __device__ __forceinline__ void wf_stage(const float2* __restrict__ x, float2* _
   }
 }
 
-// generic prime radix p (reads straight from shared memory, O(p^2) per butterfly)
-__device__ __forceinline__ void wf_stage_generic(int R, const float2* __restrict__ x, float2* __restrict__ y, const float2* __restrict__ tw, int N, int Ns) {
+// generic prime radix p (reads straight from shared memory, O(p) per output).  One work item per OUTPUT (j, q), so
+// a large prime (nfft = 4 * 67: four butterflies of 67 points) still spreads over the whole block / warp.
+__device__ __forceinline__ void wf_stage_generic(int R, const float2* __restrict__ x, float2* __restrict__ y, const float2* __restrict__ tw, int N, int Ns,
+                                                 int first, int stride) {
   const int nb = N / R, tstep = N / (Ns * R), rstep = N / R;
-  for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+  for (int idx = first; idx < N; idx += stride) {
+    const int j = idx % nb, q = idx / nb;
     const int k = j % Ns;
     const int j0 = (j - k) * R + k;
-    for (int q = 0; q < R; q++) {
-      float2 acc = x[j];
-      for (int r = 1; r < R; r++) {
-        float2 a = x[j + r * nb];
-        const float2 w1 = tw[(int)(((long long)r * k * tstep) % N)];
-        const float2 w2 = tw[((q * r) % R) * rstep];
-        const float2 w = make_float2(w1.x * w2.x - w1.y * w2.y, w1.x * w2.y + w1.y * w2.x);
-        acc.x += a.x * w.x - a.y * w.y;
-        acc.y += a.x * w.y + a.y * w.x;
-      }
-      y[j0 + q * Ns] = acc;
+    float2 acc = x[j];
+    int t1 = 0, t2 = 0;   // (r k tstep) mod N and ((q r) mod R) rstep, stepped instead of multiplied
+    for (int r = 1; r < R; r++) {
+      t1 += k * tstep; if (t1 >= N) t1 -= N;
+      t2 += q * rstep; if (t2 >= N) t2 -= N;
+      const float2 a = x[j + r * nb];
+      const float2 w1 = tw[t1], w2 = tw[t2];
+      const float2 w = make_float2(w1.x * w2.x - w1.y * w2.y, w1.x * w2.y + w1.y * w2.x);
+      acc.x += a.x * w.x - a.y * w.y;
+      acc.y += a.x * w.y + a.y * w.x;
     }
+    y[j0 + q * Ns] = acc;
   }
 }
 
@@ -164,7 +167,7 @@ static __global__ void __launch_bounds__(1024) wf_accumulate_kernel(WfParams p) 
       else if (R == 2) wf_stage<2>(x, y, p.twiddle, p.nfft, Ns);
       else if (R == 3) wf_stage<3>(x, y, p.twiddle, p.nfft, Ns);
       else if (R == 5) wf_stage<5>(x, y, p.twiddle, p.nfft, Ns);
-      else wf_stage_generic(R, x, y, p.twiddle, p.nfft, Ns);
+      else wf_stage_generic(R, x, y, p.twiddle, p.nfft, Ns, threadIdx.x, blockDim.x);
       Ns *= R;
       float2* tmp = x; x = y; y = tmp;
       __syncthreads();
@@ -271,23 +274,7 @@ static __global__ void __launch_bounds__(32 * WFW_WARPS) wf_accumulate_warp_kern
       else if (R == 2) wf_stage_warp<2>(x, y, tw, N, Ns, inv, lane);
       else if (R == 3) wf_stage_warp<3>(x, y, tw, N, Ns, inv, lane);
       else if (R == 5) wf_stage_warp<5>(x, y, tw, N, Ns, inv, lane);
-      else {   // other primes: O(R^2) butterfly straight from shared memory
-        const int nb = N / R, tstep = N / (Ns * R), rstep = N / R;
-        for (int j = lane; j < nb; j += 32) {
-          const int k = j % Ns, j0 = (j - k) * R + k;
-          for (int q = 0; q < R; q++) {
-            float2 sum = x[j];
-            for (int r = 1; r < R; r++) {
-              const float2 v = x[j + r * nb];
-              const float2 w1 = tw[r * k * tstep], w2 = tw[((q * r) % R) * rstep];
-              const float2 ww = make_float2(w1.x * w2.x - w1.y * w2.y, w1.x * w2.y + w1.y * w2.x);
-              sum.x += v.x * ww.x - v.y * ww.y;
-              sum.y += v.x * ww.y + v.y * ww.x;
-            }
-            y[j0 + q * Ns] = sum;
-          }
-        }
-      }
+      else wf_stage_generic(R, x, y, tw, N, Ns, lane, 32);   // other primes
       Ns *= R;
       float2* tmp = x; x = y; y = tmp;
       __syncwarp();
@@ -408,8 +395,6 @@ struct Waterfall {
       else pr++;
     }
     if (radix.size() > 16) return fail(PMR446_EINVAL, "waterfall width has too many prime factors");
-    for (int r : radix)
-      if (r > 61) return fail(PMR446_EINVAL, "waterfall width has a prime factor > 61");
     std::vector<float> w = design::asgram_window(W);
     std::vector<float2> tw(nfft);
     for (unsigned k = 0; k < nfft; k++) {

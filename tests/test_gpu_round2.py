@@ -1,0 +1,195 @@
+"""Round-2 GPU parity cases (VERDICT r01 "next round" item 1):
+
+ * the block-per-transform waterfall kernel (nfft > 1024, /root/reference/src/sdr_pmr446.c:473-477, :910-913 with the
+   terminal width W as asgramcf_create's argument) for W in {300, 512, 1600}, the warp kernel's largest plan (W = 250,
+   nfft = 1000 = 4 * 2 * 5^3), and a width whose nfft has a large prime factor (W = 67);
+ * BASELINE configs[3] as written: 20 Msps cf32, 1600 channels AND the W = 1600 waterfall in the same run;
+ * BASELINE configs[0] and configs[1] at their stated length (10 s captures, the reference's chunk sizes);
+ * the saturating s16 conversion at the reference's default audio_gain = 4;
+ * a failed execute (ld too small) leaves the stream state untouched.
+"""
+import numpy as np
+import pytest
+
+from util import PCM_TOL_LSB, REL_RMS_TOL, active_channels, rel_rms
+
+pytestmark = pytest.mark.gpu
+
+
+def _waterfall_pair(fs, n, chunk, W, fmt_cu8=True, M=16, carriers=None, seed=446):
+    from oracle import oracle as orc
+    from sdr_pmr446_b200 import chain, synth
+    spec = synth.CaptureSpec(fs=float(fs), num_channels=M, carriers=carriers) if carriers else synth.CaptureSpec(fs=float(fs), num_channels=M)
+    iq = synth.make_cu8(spec, n, seed) if fmt_cu8 else synth.make_cf32(spec, n, seed)
+    fmt = 1 if fmt_cu8 else 0
+    gpu = chain.PmrBatch(n_streams=1, fs_in=fs, in_fmt=fmt, num_channels=M, audio_gain=1.0, max_chunk=chunk, waterfall=W)
+    g = gpu.run(iq[None, :], chunk, want=("res", "ascii"))
+    gpu.close()
+    o = orc.PmrOracle(fs_in=fs, in_fmt=fmt, num_channels=M, audio_gain=1.0, chunk=chunk, waterfall=W)
+    r = o.run(iq, chunk, want=("res", "ascii"))
+    o.close()
+    return g, r
+
+
+def _check_waterfall(g, r, W):
+    assert g["ny"] == r["ny"]
+    assert g["psd"].shape[1:] == r["psd"].shape and r["psd"].shape[-1] == 4 * W
+    # dB values of every bin of every row, the peak (value, frequency) and the characters; a character may flip only
+    # where the 4-bin column value sits on a 2 dB level edge
+    assert np.max(np.abs(g["psd"][0] - r["psd"])) < 0.02
+    assert np.max(np.abs(g["peak"][0] - r["peak"])) < 0.02
+    mism = int(np.sum(g["ascii"][0] != r["ascii"]))
+    assert mism <= max(2, r["ascii"].size // 200), mism
+
+
+@pytest.mark.parametrize("W", [250, 300, 512, 1600])
+def test_waterfall_large_widths(W):
+    """W = 250 is the warp kernel's largest mixed-radix plan; 300 / 512 / 1600 (nfft 1200 / 2048 / 6400) run the
+    block-per-transform kernel, 6400 with its 1024-thread launch and the radix-4 lead stage folded into the load."""
+    g, r = _waterfall_pair(1024000, 300000, 100000, W)
+    _check_waterfall(g, r, W)
+
+
+def test_waterfall_width_with_large_prime_factor():
+    """asgramcf_create accepts any width: W = 67 gives nfft = 268 = 4 * 67 (generic radix-67 butterfly)."""
+    g, r = _waterfall_pair(1024000, 200000, 100000, 67)
+    _check_waterfall(g, r, 67)
+
+
+def test_cfg4_wideband_1600_channels_with_waterfall_1600():
+    """BASELINE configs[3] as written (shortened to 0.04 s): 20 Msps cf32 -> 1600-channel PFB + per-channel NBFM demod
+    AND the W = 1600 waterfall (nfft 6400) on the same resampled stream."""
+    from oracle import oracle as orc
+    from sdr_pmr446_b200 import chain, synth
+    M, fs, n, W = 1600, 20_000_000, 800_000, 1600
+    car = (synth.Carrier(3, 0.2, 1000.0, 67.0), synth.Carrier(800, 0.1, 600.0, 88.5),
+           synth.Carrier(801, 0.15, 1700.0, 123.0), synth.Carrier(1599, 0.05, 2400.0, 250.3))
+    iq = synth.make_cf32(synth.CaptureSpec(fs=float(fs), num_channels=M, carriers=car), n, 446)
+    want = ("chan", "demod", "pcm", "ascii")
+    gpu = chain.PmrBatch(n_streams=1, fs_in=fs, in_fmt=0, num_channels=M, max_chunk=400000, waterfall=W)
+    g = gpu.run(iq[None, :], 400000, want)
+    gpu.close()
+    o = orc.PmrOracle(fs_in=fs, in_fmt=0, num_channels=M, chunk=400000, waterfall=W)
+    r = o.run(iq, 400000, want)
+    o.close()
+    assert g["ns"] == r["ns"] == n // M
+    assert rel_rms(g["chan"][0], r["chan"]) < REL_RMS_TOL
+    for c in active_channels(car):
+        sl = slice(1, None) if g["demod"][0, c, 0] == r["demod"][c, 0] else slice(500, None)
+        assert rel_rms(g["demod"][0, c, sl], r["demod"][c, sl]) < REL_RMS_TOL, ("demod", c)
+    _check_waterfall(g, r, W)
+
+
+def test_cfg1_full_length_10s_1024k():
+    """BASELINE configs[0] at its stated length: 10 s of 1.024 Msps cu8 (10 240 000 samples, 103 chunks of 100 000 like
+    SDR_INPUT_CHUNK, src/sdr_pmr446.c:30), 4 FM carriers + CTCSS: counts, channelizer output and s16 audio."""
+    from oracle import oracle as orc
+    from sdr_pmr446_b200 import chain, synth
+    fs, n, chunk = 1024000, 10_240_000, 100000
+    car = synth.CFG1_CARRIERS
+    iq = synth.make_cu8(synth.CaptureSpec(fs=float(fs), carriers=car), n, 446)
+    gpu = chain.PmrBatch(n_streams=1, fs_in=fs, in_fmt=1, audio_gain=1.0, max_chunk=chunk)
+    g = gpu.run(iq[None, :], chunk, want=("chan", "pcm"))
+    gpu.close()
+    o = orc.PmrOracle(fs_in=fs, in_fmt=1, audio_gain=1.0, chunk=chunk)
+    r = o.run(iq, chunk, want=("chan", "pcm"))
+    o.close()
+    assert g["ny"] == r["ny"] and abs(g["ny"] - 2_000_000) <= 1 and g["ns"] == r["ns"] == 125_000
+    assert rel_rms(g["chan"][0], r["chan"]) < REL_RMS_TOL
+    for c in active_channels(car):
+        assert rel_rms(g["chan"][0, c], r["chan"][c]) < REL_RMS_TOL, ("chan", c)
+        dp = np.abs(g["pcm"][0, c, 700:].astype(np.int32) - r["pcm"][c, 700:].astype(np.int32))
+        assert dp.max() <= PCM_TOL_LSB, ("pcm", c, int(dp.max()))
+
+
+def test_cfg2_full_length_10s_dsd_2400k():
+    """BASELINE configs[1] at its stated length: 10 s of 2.4 Msps cu8 through the dsd_in chain in the reference's
+    200 000-sample chunks (src/dsd_in.c:25) -> 48 kHz s16."""
+    from oracle import oracle as orc
+    from sdr_pmr446_b200 import chain, synth
+    fs, n, chunk = 2400000, 24_000_000, 200000
+    iq = synth.cfg2_capture(n=n)
+    gpu = chain.DsdBatch(n_streams=1, fs_in=fs, in_fmt=1, max_chunk=chunk)
+    g = gpu.run(iq[None, :], chunk)
+    gpu.close()
+    o = orc.DsdOracle(fs_in=fs, in_fmt=1, chunk=chunk)
+    r = o.run(iq, chunk)
+    o.close()
+    assert g["ny"] == r["ny"] and g["nz"] == r["nz"]
+    assert abs(g["nz"] - 480_000) <= 8
+    assert rel_rms(g["res"][0], r["res"]) < REL_RMS_TOL
+    sl = slice(1, None) if g["fm"][0, 0] == r["fm"][0] else slice(64, None)
+    assert rel_rms(g["fm"][0, sl], r["fm"][sl]) < REL_RMS_TOL
+    dp = np.abs(g["pcm"][0, 256:].astype(np.int32) - r["pcm"][256:].astype(np.int32))
+    assert dp.max() <= PCM_TOL_LSB, int(dp.max())
+
+
+def test_default_gain_saturates_instead_of_wrapping():
+    """audio_gain = 4 is the reference's default (src/sdr_pmr446.c:33): a +-2.5 kHz deviation tone reaches +-1.6 of full
+    scale.  The s16 output must clip (like the audio device clips RtAudio's float32), never wrap, and still equal the
+    oracle's within 1 LSB."""
+    from oracle import oracle as orc
+    from sdr_pmr446_b200 import chain, synth
+    fs, n = 1024000, 300000
+    car = synth.CFG1_CARRIERS
+    iq = synth.make_cu8(synth.CaptureSpec(fs=float(fs), carriers=car), n, 446)
+    gpu = chain.PmrBatch(n_streams=1, fs_in=fs, in_fmt=1, max_chunk=100000)           # default gain
+    assert gpu.cfg.audio_gain == 4.0
+    g = gpu.run(iq[None, :], 100000, want=("audio", "pcm"))
+    gpu.close()
+    o = orc.PmrOracle(fs_in=fs, in_fmt=1, audio_gain=4.0, chunk=100000)
+    r = o.run(iq, 100000, want=("audio", "pcm"))
+    o.close()
+    clipped = 0
+    for c in active_channels(car):
+        a, p = g["audio"][0, c, 700:], g["pcm"][0, c, 700:].astype(np.int32)
+        over = np.abs(a) > 1.001
+        clipped += int(over.sum())
+        assert np.all(p[over] == np.where(a[over] > 0, 32767, -32768))                   # clipped, same sign as the audio
+        dp = np.abs(p - r["pcm"][c, 700:].astype(np.int32))
+        assert dp.max() <= PCM_TOL_LSB, (c, int(dp.max()))
+    assert clipped > 1000
+
+
+def test_failed_execute_leaves_state_untouched():
+    """A call rejected for a too-small leading dimension must not consume the chunk: the same data fed
+    again with a valid `ld` gives exactly what an undisturbed handle gives."""
+    import ctypes as C
+
+    from sdr_pmr446_b200 import chain, synth
+    from sdr_pmr446_b200._lib import ERANGE, Outputs, lib
+    fs, n = 2400000, 240000
+    iq = synth.make_cu8(synth.CaptureSpec(fs=float(fs)), 2 * n, 446)[None, :]
+    a = chain.PmrBatch(n_streams=1, fs_in=fs, in_fmt=1, audio_gain=1.0, max_chunk=n)
+    b = chain.PmrBatch(n_streams=1, fs_in=fs, in_fmt=1, audio_gain=1.0, max_chunk=n)
+    first_a = a.execute(iq[:, :2 * n], want=("pcm",))
+    first_b = b.execute(iq[:, :2 * n], want=("pcm",))
+    assert np.array_equal(first_a["pcm"], first_b["pcm"])
+    # rejected call on b: pcm requested with ld = 10
+    bad = Outputs()
+    pcm = np.zeros((1, 16, 10), np.int16)
+    bad.pcm, bad.ld = pcm.ctypes.data, 10
+    chunk2 = np.ascontiguousarray(iq[:, 2 * n:])
+    rc = lib().pmr446_batch_execute(b.h, chunk2.ctypes.data, chunk2.strides[0], n, C.byref(bad), None, None)
+    assert rc == ERANGE
+    second_a = a.execute(chunk2, want=("pcm",))
+    second_b = b.execute(chunk2, want=("pcm",))
+    a.close()
+    b.close()
+    assert second_a["ns"] == second_b["ns"]
+    assert np.array_equal(second_a["pcm"], second_b["pcm"])
+    # dsd_in path
+    da = chain.DsdBatch(n_streams=1, fs_in=fs, in_fmt=1, max_chunk=n)
+    db = chain.DsdBatch(n_streams=1, fs_in=fs, in_fmt=1, max_chunk=n)
+    da.execute(iq[:, :2 * n])
+    db.execute(iq[:, :2 * n])
+    from sdr_pmr446_b200._lib import DsdOutputs
+    dbad = DsdOutputs()
+    small = np.zeros((1, 8), np.int16)
+    dbad.pcm, dbad.out_ld, dbad.res_ld = small.ctypes.data, 8, 0
+    rc = lib().dsd446_batch_execute(db.h, chunk2.ctypes.data, chunk2.strides[0], n, C.byref(dbad), None, None)
+    assert rc == ERANGE
+    ra, rb = da.execute(chunk2), db.execute(chunk2)
+    da.close()
+    db.close()
+    assert ra["nz"] == rb["nz"] and np.array_equal(ra["pcm"], rb["pcm"])

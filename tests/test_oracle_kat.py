@@ -203,7 +203,7 @@ def test_pmr_chain_end_to_end_tones():
         # (the 2.4 kHz tone on channel 15 fills the 12.5 kHz channel and sits on the resampler's skirt: looser)
         assert abs(r["demod"][ch, 4000:].std() - np.sqrt(0.4 ** 2 + 0.08 ** 2) / np.sqrt(2)) < (0.01 if ch != 14 else 0.03)
         # the 377-tap high-pass removes the CTCSS tone: what is left is the audio tone through de-emphasis
-        assert np.array_equal(r["pcm"][ch], (r["audio"][ch] * np.float32(32767.0)).astype(np.int32).astype(np.int16))
+        assert np.array_equal(r["pcm"][ch], np.clip((r["audio"][ch] * np.float32(32767.0)).astype(np.int32), -32768, 32767).astype(np.int16))
 
 
 def test_lpcomp_is_the_ctcss_branch():
@@ -303,3 +303,19 @@ def test_fir_deemphasis_is_six_db_per_octave():
     # (-0.28 dB between the two tones) and the channel filter are common to both variants and cancel in the difference.
     assert abs((fir_db - iir_db) + 5.21) < 0.15, (fir_db, iir_db)
     assert abs(iir_db + 0.83 + 0.28) < 0.25, iir_db
+
+
+def test_pmr_s16_saturates_at_default_gain():
+    """The PMR chain's s16 output clips at full scale (the reference's float audio is clipped by the audio device);
+    only dsd_in's conversion is the plain C cast (src/dsd_in.c:172-175)."""
+    from sdr_pmr446_b200 import synth
+    iq = synth.make_cu8(synth.CaptureSpec(fs=1024000.0, carriers=synth.CFG1_CARRIERS), 200000, 446)
+    o = orc.PmrOracle(fs_in=1024000, in_fmt=1, audio_gain=4.0, chunk=100000)
+    r = o.run(iq, 100000, want=("audio", "pcm"))
+    o.close()
+    a, p = r["audio"][6, 700:], r["pcm"][6, 700:].astype(np.int32)
+    over = np.abs(a) > 1.001
+    assert over.sum() > 100
+    assert np.all(p[over] == np.where(a[over] > 0, 32767, -32768))
+    inside = np.abs(a) < 0.999
+    assert np.all(p[inside] == np.trunc(a[inside] * np.float32(32767.0)).astype(np.int32))
