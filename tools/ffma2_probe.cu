@@ -1,0 +1,81 @@
+// Micro-benchmark (run on the B200 box): issue rate of Blackwell's packed FP32 FMA (fma.rn.f32x2 -> SASS FFMA2) against the
+// scalar FFMA, alone and interleaved with ALU-pipe work, to decide how the FIR kernels should be written.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/ffma2_probe tools/ffma2_probe.cu && /tmp/ffma2_probe
+#include <cuda_runtime.h>
+#include <cstdio>
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(*(unsigned long long*)&d) : "l"(*(unsigned long long*)&a), "l"(*(unsigned long long*)&b), "l"(*(unsigned long long*)&c));
+  return d;
+}
+struct Taps { float h[16]; };
+
+template <int MODE>
+__global__ void __launch_bounds__(256) probe(float* out, int iters, Taps tp, float a, float b) {
+  float2 x[8];
+  unsigned m[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { x[i] = make_float2((float)(threadIdx.x + i), (float)(threadIdx.x * 2 + i)); m[i] = threadIdx.x * 7 + i; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        if (MODE == 0) { x[i].x = fmaf(x[i].x, a, b); x[i].y = fmaf(x[i].y, a, b); }                       // 2 FFMA, register operands
+        if (MODE == 1) { x[i].x = fmaf(x[i].x, tp.h[u], b); x[i].y = fmaf(x[i].y, tp.h[u], b); }           // 2 FFMA, constant-bank tap
+        if (MODE == 2) x[i] = ffma2(x[i], make_float2(a, b), make_float2(b, a));                            // FFMA2, register pairs
+        if (MODE == 3) x[i] = ffma2(x[i], make_float2(tp.h[u], tp.h[u]), make_float2(b, b));                // FFMA2, uniform-register tap
+        if (MODE == 4) { x[i] = ffma2(x[i], make_float2(tp.h[u], tp.h[u]), make_float2(b, b)); m[i] = __byte_perm(m[i], m[(i + 1) & 7], 0x2103); }   // + 1 PRMT
+        if (MODE == 5) { x[i].x = fmaf(x[i].x, tp.h[u], b); x[i].y = fmaf(x[i].y, tp.h[u], b); m[i] = __byte_perm(m[i], m[(i + 1) & 7], 0x2103); }   // 2 FFMA + 1 PRMT
+        if (MODE == 6) { x[i] = ffma2(x[i], make_float2(tp.h[u], tp.h[u]), make_float2(b, b)); m[i] = __byte_perm(m[i], m[(i + 1) & 7], 0x2103); m[(i + 3) & 7] += m[i]; }   // + PRMT + IADD
+        if (MODE == 7) { x[i] = ffma2(x[i], make_float2(a, a), make_float2(b, b)); }                        // FFMA2, scalar register broadcast
+      }
+    }
+  }
+  float s = 0.0f;
+  unsigned q = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { s += x[i].x + x[i].y; q += m[i]; }
+  if (s == 12345.678f || q == 0x12345678u) out[0] = s + (float)q;
+}
+
+template <int MODE>
+static void run(const char* name, int sms) {
+  float* d;
+  cudaMalloc(&d, 4);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  Taps tp;
+  for (int i = 0; i < 16; i++) tp.h[i] = 0.999f - 0.0001f * i;
+  const int iters = 2048, blocks = sms * 8;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; rep++) {
+    cudaEventRecord(e0);
+    probe<MODE><<<blocks, 256>>>(d, iters, tp, 0.999f, 0.001f);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double fma = 2.0 * 8 * 16 * (double)iters * 256.0 * blocks;   // scalar FMAs
+    const double tf = 2.0 * fma / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  printf("{\"mode\": \"%s\", \"tflops\": %.2f}\n", name, best);
+  cudaFree(d);
+}
+
+int main() {
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  run<0>("ffma_reg", sms);
+  run<1>("ffma_const_tap", sms);
+  run<2>("ffma2_regpair", sms);
+  run<3>("ffma2_uniform_tap", sms);
+  run<7>("ffma2_scalar_reg_broadcast", sms);
+  run<4>("ffma2_uniform_tap+1prmt", sms);
+  run<5>("2ffma_const_tap+1prmt", sms);
+  run<6>("ffma2_uniform_tap+prmt+iadd", sms);
+  return cudaDeviceSynchronize() != cudaSuccess;
+}
