@@ -3,25 +3,29 @@
 // (nco_crcf_mix_down/step, firpfbch_crcf_analyzer_execute, transpose) and
 // freqdem_demodulate_block (:881) for every channel.
 //
-// One warp walks a tile of 140 frames of one stream in five batches of 28 frames.
-//  Phase A (two frames per step): lane l = (branch i = l & 15, half h = l >> 4); the 26-tap branch filter is split
-//   in two 13-tap halves so that each lane keeps only a 14-slot window in registers (rotation period 14 frames =
-//   7 steps, the unrolled loop body).  Half 1 runs on the same sample stream delayed by 13 frames, so both halves
-//   execute the same code.  The commutator sends resampled sample 16f + 15 - i to branch i; the NCO phasor of a lane
-//   only depends on the frame parity when 32 dtheta = 0 mod 2^32 (the reference's 17/32-cycle step), so mixing is one
-//   complex multiply by a per-lane constant.  The halves swap one partial sum per step and the finished dot product
-//   of frame k goes to shared memory, row k, column n = 15 - i (the DFT input index).
-//  Phase B: lane = frame: reads its 16 branch outputs (row stride 17: conflict-free), runs the forward 16-point DFT in
-//   registers (no shuffles) and writes channel-major rows [channel][1 + frame] (row stride 29).
-//  Phase C: lane = (channel, 14 consecutive frames): discriminator arg(conj(y[f-1]) y[f]) with a polynomial atan2
-//   (|err| < 3e-7 rad) and aligned two-sample stores into the channel's ring row; column 0 of each row carries the
-//   last frame of the previous batch.
-// The warp owns its shared-memory slice, so the phases are separated by __syncwarp() only.
+// Round-2 mapping (round 1: one sample per lane and frame, 1.47 ms per 1024-stream step, 98 warp instructions per frame):
+// one warp walks a tile of 160 frames of one stream in five batches of 32 frames, all in its own shared-memory slice.
+//  Staging: the batch's 32 new frames (16 samples each) go from the 200 kHz ring to shared memory with 128-bit loads;
+//   on the way in each sample gets (a) the zero-input part of the front end's DC blocker when the fused front end left
+//   it to its consumer (Correction, frontend.cuh) and (b) the NCO phasor -- theta_j = j dtheta only depends on j mod 32
+//   when 32 dtheta = 0 mod 2^32 (the reference's 17/32-cycle step), so a lane multiplies by four constants.  The 25
+//   frames of filter history are kept from the previous batch.
+//  Phase A (branch filters): lane = (branch i, half g): 8 consecutive frames of its branch per pass from a 33-sample
+//   register window, all 26 taps in registers, one packed FFMA2 per complex tap (scalar-broadcast operand); two passes
+//   cover the lane's 16 frames.  The commutator sends resampled sample 16 f + 15 - i to branch i; the dot product of
+//   frame f goes to shared memory row f, column n = 15 - i (the DFT input index).
+//  Phase B + C: lane = frame: 16-point forward DFT in registers, the previous frame's channel values by shuffle (lane 0
+//   takes the last frame of the previous batch from shared memory), discriminator arg(conj(y[f-1]) y[f]) with a polynomial
+//   atan2 (|err| < 3e-7 rad), and for every channel ONE coalesced 128-byte store of 32 consecutive frames into the
+//   channel's ring row -- no transpose pass.
+// Frame 0 of a tile only provides the "previous frame" of frame 1, so a tile owns 159 frames.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "audio_fft.cuh"   // dft16 / af_dig
+#include "frontend.cuh"    // Correction
+#include "frontend_fused.cuh"   // packed FP32 helpers
 
 namespace pmr {
 
@@ -40,14 +44,20 @@ struct ChanParams {
   long long demod_stride, demod_mask;
   float2* chan;            // optional: [n_streams][16][chan_ld], column = f - f0
   long long chan_ld;
+  Correction corr;         // zero-input response of the front end's DC blocker still to be added to ring samples >= corr.from
 };
 struct ChanTaps {          // selector taps, only read by the TAPS instantiation
   float* mag_part;         // optional: [n_streams][tiles][16] sum of |y| over the owned frames of each tile (RSSI, :330-336)
   float2* edge;            // optional: [n_streams][16][2] channel sample of the first (f0) and last (f1 - 1) owned frame
 };
 
-constexpr int CH_TL = 136;      // owned frames per tile
-constexpr int CH_BODIES = 10;   // 10 bodies x 14 frames = 140 computed frames, starting 4 before the tile
+constexpr int CH_NB = 5;                      // batches per tile
+constexpr int CH_FR = 32 * CH_NB;             // computed frames per tile
+constexpr int CH_TL = CH_FR - 1;              // owned frames per tile
+constexpr int CH_HIST = 25;                   // frames of branch-filter history in front of a batch (26 taps)
+constexpr int CH_XN = (CH_HIST + 32) * 16;    // float2 per sample buffer: 57 frames
+constexpr int CH_V_STRIDE = 17;               // float2 per frame row of the branch-output buffer (16 + 1 pad)
+constexpr int CH_SMEM_WARP = CH_XN + 32 * CH_V_STRIDE + 16;   // + the previous batch's last frame (16 channels)
 
 // atan2 by a degree-17 odd minimax polynomial on [0, 1] (Abramowitz & Stegun 4.4.49, |err| <= 2e-8 in
 // exact arithmetic, < 3e-7 rad in float32); (0, 0) falls back to libm for the signed-zero cases.
@@ -72,192 +82,236 @@ __device__ __forceinline__ float fast_atan2f(float y, float x) {
   if (__float_as_int(x) < 0) r = 3.14159265358979324f - r;
   return copysignf(r, y);
 }
+// two at once: the quotient and the quadrant logic stay scalar, the polynomial runs packed (9 FFMA2 for two arguments)
+__device__ __forceinline__ float2 fast_atan2f_x2(float y0, float x0, float y1, float x1) {
+  const float ax0 = fabsf(x0), ay0 = fabsf(y0), ax1 = fabsf(x1), ay1 = fabsf(y1);
+  const float mx0 = fmaxf(ax0, ay0), mn0 = fminf(ax0, ay0), mx1 = fmaxf(ax1, ay1), mn1 = fminf(ax1, ay1);
+  const float2 a = make_float2(__fdividef(mn0, mx0 == 0.0f ? 1.0f : mx0), __fdividef(mn1, mx1 == 0.0f ? 1.0f : mx1));
+  const float2 s = fmul2(a, a);
+  auto k2 = [](float c) { return make_float2(c, c); };
+  float2 r = k2(0.0028662257f);
+  r = ffma2(r, s, k2(-0.0161657367f));
+  r = ffma2(r, s, k2(0.0429096138f));
+  r = ffma2(r, s, k2(-0.0752896400f));
+  r = ffma2(r, s, k2(0.1065626393f));
+  r = ffma2(r, s, k2(-0.1420889944f));
+  r = ffma2(r, s, k2(0.1999355085f));
+  r = ffma2(r, s, k2(-0.3333314528f));
+  r = ffma2(r, s, k2(1.0f));
+  r = fmul2(r, a);
+  if (ay0 > ax0) r.x = 1.57079632679489662f - r.x;
+  if (ay1 > ax1) r.y = 1.57079632679489662f - r.y;
+  if (__float_as_int(x0) < 0) r.x = 3.14159265358979324f - r.x;
+  if (__float_as_int(x1) < 0) r.y = 3.14159265358979324f - r.y;
+  return make_float2(copysignf(r.x, y0), copysignf(r.y, y1));
+}
 
-constexpr int CH_BATCH = 28;               // frames per batch: two rotations of the 14-slot window
-constexpr int CH_NB = 5;                   // batches per tile (140 computed frames)
-constexpr int CH_A_STRIDE = 17;            // float2 per frame row of the branch-output buffer (16 + 1 pad)
-constexpr int CH_B_STRIDE = 29;            // float2 per channel row of the channel-output buffer (1 previous + 28)
-constexpr int CH_SMEM_WARP = CH_BATCH * CH_A_STRIDE + 16 * CH_B_STRIDE;
-
-template <bool TAPS> struct TapState { float macc = 0.0f; int k_first = -1, k_last = -1; };
+template <bool TAPS> struct TapState { float macc[16]; };
 template <> struct TapState<false> {};
 
 // TAPS = the selector taps (mag_part / edge) are wanted: a separate instantiation, so that the throughput path carries
 // none of their registers.
 template <bool NCO_CONST, bool TAPS>
-__global__ void __launch_bounds__(128, TAPS ? 4 : 5) channelize16_kernel(ChanParams p, ChanTaps tp) {
-  __shared__ float2 ch_smem[4 * CH_SMEM_WARP];
-  const int lane = threadIdx.x & 31, br = lane & 15, hsel = lane >> 4;
+__global__ void __launch_bounds__(128, 4) channelize16_kernel(ChanParams p, ChanTaps tp) {
+  __shared__ __align__(16) float2 ch_smem[4 * CH_SMEM_WARP];
+  const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp >= (long long)p.n_streams * p.tiles) return;   // warp-uniform
-  float2* A = ch_smem + (threadIdx.x >> 5) * CH_SMEM_WARP;   // [frame of the batch][DFT input n]
-  float2* B = A + CH_BATCH * CH_A_STRIDE;                     // [channel][previous frame, 28 frames]
+  float2* const X = ch_smem + (threadIdx.x >> 5) * CH_SMEM_WARP;   // [57 frames][16 samples], mixed
+  float2* const V = X + CH_XN;                                     // [32 frames][17]: branch outputs, column = DFT input index
+  float2* const carry = V + 32 * CH_V_STRIDE;                      // [16] channel values of the previous batch's last frame
   const int s = (int)(warp / p.tiles);
-  const long long tile = p.tile0 + (warp % p.tiles);
-  const long long fa = tile * CH_TL, fs = fa - 4;          // computed frames are fs + k, k in [0, 140)
+  const int tile_idx = (int)(warp % p.tiles);
+  const long long fa = (p.tile0 + tile_idx) * CH_TL, fs = fa - 1;  // computed frames are fs + k, k in [0, 160)
   const float2* res = p.res + (long long)s * p.res_stride;
 
-  float h[13];
+  // ---- staging bounds, 32-bit and relative to J0 = index of the sample X[0] of batch 0 ------------------------------------
+  const long long J0 = 16 * (fs - CH_HIST);
+  auto clampi = [](long long v) { return (int)(v < -(1 << 29) ? -(1 << 29) : (v > (1 << 29) ? (1 << 29) : v)); };
+  const int lo_rel = clampi(-J0);               // samples with jrel < lo_rel lie before the stream start: zero
+  const int hi_rel = clampi(p.r1 - J0);         // samples with jrel >= hi_rel do not exist yet: zero
+  const unsigned j0_32 = (unsigned)J0, rmask = (unsigned)p.res_mask;
+  const Correction& cr = p.corr;
+  const float2* vrow = cr.v_seg ? cr.v_seg + (long long)s * cr.nseg : nullptr;
+  const int from_rel = clampi(cr.from - J0), seg_rel0 = clampi(J0 - cr.seg0_out);
+  const unsigned smask = (1u << cr.seg_shift) - 1u;
+  const float nalpha = -cr.alpha;
+  // NCO phasors (A.7): theta_j = j dtheta mod 2^32.  A lane always stages samples with the same j mod 32 per region
+  // (history region: X index 2 lane + 64 i; new-frame region: 400 + 2 lane + 64 i), so four constants when 32 dtheta = 0.
+  float pcs[2][2], psn[2][2];
+  if (NCO_CONST) {
 #pragma unroll
-  for (int n = 0; n < 13; n++) h[n] = __ldg(p.taps + br * 26 + 13 * hsel + n);
-
-  // phase C of every batch: this lane owns channel br, frames 14 hsel .. 14 hsel + 13 of the batch
-  float* drow = p.demod + ((long long)s * 16 + br) * p.demod_stride;
-  float2* crow = p.chan ? p.chan + ((long long)s * 16 + br) * p.chan_ld : nullptr;
-
-  // this lane's sample for (delayed) frame k: j = jb + 16 k; valid iff 0 <= j < r1
-  const long long jb = 16 * (fs - 13 * hsel) + 15 - br;
-  const unsigned jb32 = (unsigned)jb, rmask = (unsigned)p.res_mask;
-  int k_lo = -(1 << 20), k_hi = 1 << 20;
-  if (jb < 0) k_lo = (int)((-jb + 15) / 16);
-  {
-    const long long t = p.r1 - jb;   // j < r1  <=>  16 k < t
-    if (t <= 0) k_hi = -(1 << 20);
-    else if (t < (1ll << 24)) k_hi = (int)((t + 15) / 16);
-  }
-  // NCO phasors (A.7): theta_j = j * dtheta mod 2^32; constant per frame parity when 32 dtheta = 0
-  float pc[2], ps[2];
+    for (int reg = 0; reg < 2; reg++)
 #pragma unroll
-  for (int par = 0; par < 2; par++) {
-    const unsigned th = (jb32 + 16u * (unsigned)par) * p.dtheta;
-    sincospif((float)(int)th * (1.0f / 2147483648.0f), &ps[par], &pc[par]);
-  }
-  auto fetch = [&](int k) -> float2 {   // branch-free: out-of-range frames read slot 0 of the ring and are zeroed
-    const bool ok = k >= k_lo && k < k_hi;
-    const unsigned idx = ok ? ((jb32 + 16u * (unsigned)k) & rmask) : 0u;
-    float2 v = res[idx];
-    if (!ok) v = make_float2(0.0f, 0.0f);
-    return v;
-  };
-  auto mix = [&](float2 v, int k, int par, float& xr, float& xi) {   // par = k & 1, passed as a literal
-    float cs, sn;
-    if (NCO_CONST) {
-      cs = pc[par]; sn = ps[par];
-    } else {
-      const unsigned th = (jb32 + 16u * (unsigned)k) * p.dtheta;
-      sincospif((float)(int)th * (1.0f / 2147483648.0f), &sn, &cs);
-    }
-    xr = fmaf(v.x, cs, v.y * sn);    // v * conj(e^{j theta})
-    xi = fmaf(v.y, cs, -v.x * sn);
-  };
-
-  // window slot of frame k is k mod 14; preload frames -12..-1 into slots 2..13
-  float wr[14], wi[14];
-  wr[0] = wi[0] = wr[1] = wi[1] = 0.0f;
-#pragma unroll
-  for (int n = 1; n <= 12; n++) mix(fetch(-n), -n, n & 1, wr[14 - n], wi[14 - n]);
-
-  // ownership of computed frame k (relative to fs), 32-bit
-  long long lo64 = (fa > p.f0 ? fa : p.f0) - fs, hi64 = ((fa + CH_TL) < p.f1 ? (fa + CH_TL) : p.f1) - fs;
-  const int own_lo = (int)(lo64 < 0 ? 0 : (lo64 > 4096 ? 4096 : lo64)), own_hi = (int)(hi64 < 0 ? 0 : (hi64 > 4096 ? 4096 : hi64));
-  const unsigned fs32 = (unsigned)fs, dmask = (unsigned)p.demod_mask;
-  const int crel = (int)(fs - p.f0 < -(1ll << 30) ? -(1 << 30) : (fs - p.f0 > (1ll << 30) ? (1 << 30) : fs - p.f0));
-  // computed frame k is absolute frame 0 (stream start: r_prime = 0) when k == k_zero
-  const int k_zero = (fs <= 0 && fs > -4096) ? (int)(-fs) : -1;
-  if (lane < 16) B[lane * CH_B_STRIDE] = make_float2(0.0f, 0.0f);   // "previous frame" of the first batch (never owned)
-
-  TapState<TAPS> ta;
-  if constexpr (TAPS) {
-    ta.k_first = (int)(p.f0 - fs > 4096 ? -1 : (p.f0 - fs < 0 ? -1 : p.f0 - fs));
-    ta.k_last = (int)(p.f1 - 1 - fs > 4096 ? -1 : (p.f1 - 1 - fs < 0 ? -1 : p.f1 - 1 - fs));
-  }
-  float2 n0 = fetch(0), n1 = fetch(1);
-#pragma unroll 1
-  for (int batch = 0; batch < CH_NB; batch++) {
-    // ---- phase A: mix, branch filters; dot products of frame kk go to A[kk][15 - branch] ----------------------------
-#pragma unroll 1
-    for (int hb = 0; hb < 2; hb++) {
-      const int kb = CH_BATCH * batch + 14 * hb;
-#pragma unroll
-      for (int j = 0; j < 7; j++) {
-        const int k = kb + 2 * j;            // frames k (slot 2j) and k + 1 (slot 2j + 1)
-        mix(n0, k, 0, wr[2 * j], wi[2 * j]);
-        mix(n1, k + 1, 1, wr[2 * j + 1], wi[2 * j + 1]);
-        n0 = fetch(k + 2);                   // one step ahead
-        n1 = fetch(k + 3);
-        float d0r = 0.0f, d0i = 0.0f, d1r = 0.0f, d1i = 0.0f;
-#pragma unroll
-        for (int n = 0; n < 13; n++) {
-          d0r = fmaf(h[n], wr[(2 * j - n + 14) % 14], d0r);
-          d0i = fmaf(h[n], wi[(2 * j - n + 14) % 14], d0i);
-          d1r = fmaf(h[n], wr[(2 * j + 1 - n + 14) % 14], d1r);
-          d1i = fmaf(h[n], wi[(2 * j + 1 - n + 14) % 14], d1i);
-        }
-        // half 0 completes frame k, half 1 frame k + 1: swap the other frame's partial sum
-        float ar = hsel ? d1r : d0r, ai = hsel ? d1i : d0i;
-        ar += __shfl_xor_sync(0xffffffffu, hsel ? d0r : d1r, 16);
-        ai += __shfl_xor_sync(0xffffffffu, hsel ? d0i : d1i, 16);
-        A[(14 * hb + 2 * j + hsel) * CH_A_STRIDE + 15 - br] = make_float2(ar, ai);
+      for (int e = 0; e < 2; e++) {
+        const unsigned th = (j0_32 + (unsigned)(reg * CH_HIST * 16 + 2 * lane + e)) * p.dtheta;
+        sincospif((float)(int)th * (1.0f / 2147483648.0f), &psn[reg][e], &pcs[reg][e]);
       }
+  }
+  // stages X[pp], X[pp + 1] (pp even) of the batch whose X[0] is sample J0 + boff
+  auto stage_pair = [&](int pp, int boff, int reg) {
+    const int jrel = boff + pp;
+    float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (jrel + 1 >= lo_rel && jrel < hi_rel) {
+      v = *(const float4*)(res + ((j0_32 + (unsigned)jrel) & rmask));   // jrel even: aligned, never straddles the ring's end
+      if (jrel < lo_rel) { v.x = 0.0f; v.y = 0.0f; }
+      if (jrel + 1 >= hi_rel) { v.z = 0.0f; v.w = 0.0f; }
+      if (vrow && jrel + 1 >= from_rel) {
+        // x -= alpha V0[segment] E[k]: the producer's segments hold an even number of ring samples, both share one
+        const int rel = seg_rel0 + jrel;
+        const int sg = rel >> cr.seg_shift;
+        if (rel >= 0 && sg < cr.nseg) {
+          const float2 v0 = vrow[sg];
+          const float2 e = *(const float2*)(cr.e + cr.halo_out + ((unsigned)rel & smask));
+          const float ax = nalpha * v0.x, ay = nalpha * v0.y;
+          if (jrel >= from_rel && jrel >= lo_rel) { v.x = fmaf(ax, e.x, v.x); v.y = fmaf(ay, e.x, v.y); }
+          if (jrel + 1 < hi_rel) { v.z = fmaf(ax, e.y, v.z); v.w = fmaf(ay, e.y, v.w); }
+        }
+      }
+      float c0, s0, c1, s1;
+      if (NCO_CONST) {
+        c0 = pcs[reg][0]; s0 = psn[reg][0]; c1 = pcs[reg][1]; s1 = psn[reg][1];
+      } else {
+        const unsigned th = (j0_32 + (unsigned)jrel) * p.dtheta;
+        sincospif((float)(int)th * (1.0f / 2147483648.0f), &s0, &c0);
+        sincospif((float)(int)(th + p.dtheta) * (1.0f / 2147483648.0f), &s1, &c1);
+      }
+      v = make_float4(fmaf(v.x, c0, v.y * s0), fmaf(v.y, c0, -v.x * s0),    // x conj(e^{j theta})
+                      fmaf(v.z, c1, v.w * s1), fmaf(v.w, c1, -v.z * s1));
     }
-    __syncwarp();
-    // ---- phase B: lane = frame of the batch: forward 16-point DFT in registers, transposed to B[channel][1 + frame] --
-    if (lane < CH_BATCH) {
-      float2 v[16];
+    *(float4*)(X + pp) = v;
+  };
+
+  // branch taps of this lane (phase A): branch i, newest sample first
+  const int br = lane & 15, half = lane >> 4;
+  float h[26];
 #pragma unroll
-      for (int n = 0; n < 16; n++) v[n] = A[lane * CH_A_STRIDE + n];
-      dft16<false>(v);
+  for (int n = 0; n < 26; n++) h[n] = __ldg(p.taps + br * 26 + n);
+
+  // ownership of computed frame k (relative to fs): [own_lo, own_hi), and never k = 0
+  long long lo64 = (fa > p.f0 ? fa : p.f0) - fs, hi64 = ((fa + CH_TL) < p.f1 ? (fa + CH_TL) : p.f1) - fs;
+  const int own_lo = (int)(lo64 < 1 ? 1 : (lo64 > 4096 ? 4096 : lo64)), own_hi = (int)(hi64 < 0 ? 0 : (hi64 > 4096 ? 4096 : hi64));
+  const unsigned fs32 = (unsigned)fs, dmask = (unsigned)p.demod_mask;
+  const int crel = clampi(fs - p.f0);
+  const int k_zero = (fs <= 0 && fs > -4096) ? (int)(-fs) : -1;   // computed frame k is absolute frame 0: r_prime = 0
+  float* const drow0 = p.demod + (long long)s * 16 * p.demod_stride;
+  float2* const crow0 = p.chan ? p.chan + (long long)s * 16 * p.chan_ld : nullptr;
+  TapState<TAPS> ta;
+  int k_first = -1, k_last = -1;
+  if constexpr (TAPS) {
 #pragma unroll
-      for (int c = 0; c < 16; c++) B[c * CH_B_STRIDE + 1 + lane] = v[af_dig(c)];
-    }
-    __syncwarp();
-    // ---- phase C: lane = (channel br, frames 14 hsel ..): discriminator (A.9) arg(conj(prev) y) * ref with separate
-    // mul/add like the C reference, two-sample stores --------------------------------------------------------------------
-    {
-      const int k0 = CH_BATCH * batch + 14 * hsel;
-      const float2* brow = B + br * CH_B_STRIDE + 14 * hsel;
-      float2 prev = brow[0];
-      const bool all = k0 >= own_lo && k0 + 14 <= own_hi;
-      // (fs + k0) is even: a pair of frames is an aligned float2 of the ring and never straddles its end
+    for (int c = 0; c < 16; c++) ta.macc[c] = 0.0f;
+    k_first = (int)(p.f0 - fs > 4096 ? -1 : (p.f0 - fs < 0 ? -1 : p.f0 - fs));
+    k_last = (int)(p.f1 - 1 - fs > 4096 ? -1 : (p.f1 - 1 - fs < 0 ? -1 : p.f1 - 1 - fs));
+  }
+
+  // batches that hold no owned frame (a chunk boundary inside the tile) are skipped: the first one needed is the one
+  // with the frame before the first owned frame, the last one the one with the last owned frame
+  const bool any = own_hi > own_lo;             // (every launched tile owns a frame; kept warp-uniform and safe anyway)
+  const int b_first = any ? (own_lo - 1) / 32 : 0, b_last = any ? (own_hi - 1) / 32 : -1;
+  if (any)
+    for (int pp = 2 * lane; pp < CH_HIST * 16; pp += 64) stage_pair(pp, 512 * b_first, 0);   // history of the first batch
+  if (lane < 16) carry[lane] = make_float2(0.0f, 0.0f);
+
 #pragma unroll 1
-      for (int i = 0; i < 14; i += 2) {
-        const float2 y0 = brow[1 + i], y1 = brow[2 + i];
-        if (k0 + i == k_zero) prev = make_float2(0.0f, 0.0f);
-        const float re0 = __fadd_rn(__fmul_rn(prev.x, y0.x), __fmul_rn(prev.y, y0.y));
-        const float im0 = __fsub_rn(__fmul_rn(prev.x, y0.y), __fmul_rn(prev.y, y0.x));
-        float2 p1 = y0;
-        if (k0 + i + 1 == k_zero) p1 = make_float2(0.0f, 0.0f);
-        const float re1 = __fadd_rn(__fmul_rn(p1.x, y1.x), __fmul_rn(p1.y, y1.y));
-        const float im1 = __fsub_rn(__fmul_rn(p1.x, y1.y), __fmul_rn(p1.y, y1.x));
-        const float2 dm = make_float2(fast_atan2f(im0, re0) * p.ref, fast_atan2f(im1, re1) * p.ref);
-        const int k = k0 + i;
-        if constexpr (TAPS) {
-          if (tp.mag_part) {
-            if (k >= own_lo && k < own_hi) ta.macc += sqrtf(fmaf(y0.x, y0.x, y0.y * y0.y));
-            if (k + 1 >= own_lo && k + 1 < own_hi) ta.macc += sqrtf(fmaf(y1.x, y1.x, y1.y * y1.y));
-          }
-          if (tp.edge) {
-            float2* e = tp.edge + ((long long)s * 16 + br) * 2;
-            if (k == ta.k_first) e[0] = y0;
-            if (k + 1 == ta.k_first) e[0] = y1;
-            if (k == ta.k_last) e[1] = y0;
-            if (k + 1 == ta.k_last) e[1] = y1;
-          }
-        }
-        float* d = drow + ((fs32 + (unsigned)k) & dmask);
-        if (all) {
-          *(float2*)d = dm;
-          if (crow) { crow[crel + k] = y0; crow[crel + k + 1] = y1; }
-        } else {
-          const bool a0 = k >= own_lo && k < own_hi, a1 = k + 1 >= own_lo && k + 1 < own_hi;
-          if (a0) d[0] = dm.x;
-          if (a1) d[1] = dm.y;
-          if (crow) {
-            if (a0) crow[crel + k] = y0;
-            if (a1) crow[crel + k + 1] = y1;
-          }
-        }
-        prev = y1;
+  for (int batch = b_first; batch <= b_last; batch++) {
+    const int boff = 512 * batch;
+    if (batch > b_first) {   // the last 25 frames of the previous batch become this batch's history
+      __syncwarp();
+      constexpr int NC = (CH_HIST * 16 / 2 + 31) / 32;   // float4 copies per lane: 200 in all
+      float4 t[NC];
+#pragma unroll
+      for (int i = 0; i < NC; i++) {
+        const int q = 2 * (lane + 32 * i);
+        if (q < CH_HIST * 16) t[i] = *(const float4*)(X + 512 + q);
       }
       __syncwarp();
-      if (hsel) B[br * CH_B_STRIDE] = prev;      // frame 27 of this batch is the next batch's previous frame
+#pragma unroll
+      for (int i = 0; i < NC; i++) {
+        const int q = 2 * (lane + 32 * i);
+        if (q < CH_HIST * 16) *(float4*)(X + q) = t[i];
+      }
+    }
+    // ---- staging: 32 new frames = 512 samples, 8 pairs per lane --------------------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < 8; i++) stage_pair(CH_HIST * 16 + 2 * lane + 64 * i, boff, 1);
+    __syncwarp();
+    // ---- phase A: branch filters.  Frame kk of the batch sits in X frames kk .. kk + 25 (newest last) --------------------------
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+      const int kk0 = 16 * half + 8 * pass;
+      const float2* xb = X + kk0 * 16 + (15 - br);
+      float2 w[33];
+#pragma unroll
+      for (int q = 0; q < 33; q++) w[q] = xb[16 * q];
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int n = 0; n < 26; n++) acc = fma_tap(h[n], w[25 + r - n], acc);
+        V[(kk0 + r) * CH_V_STRIDE + 15 - br] = acc;
+      }
     }
     __syncwarp();
+    // ---- phase B + C: lane = frame kk = 32 batch + lane ------------------------------------------------------------------------
+    {
+      float2 v[16];
+#pragma unroll
+      for (int n = 0; n < 16; n++) v[n] = V[lane * CH_V_STRIDE + n];
+      dft16<false>(v);
+      const int kk = 32 * batch + lane;
+      const bool own = kk >= own_lo && kk < own_hi;
+      const unsigned col = (fs32 + (unsigned)kk) & dmask;
+#pragma unroll
+      for (int c = 0; c < 16; c += 2) {
+        const float2 y0 = v[af_dig(c)], y1 = v[af_dig(c + 1)];
+        float2 p0, p1;
+        p0.x = __shfl_up_sync(0xffffffffu, y0.x, 1); p0.y = __shfl_up_sync(0xffffffffu, y0.y, 1);
+        p1.x = __shfl_up_sync(0xffffffffu, y1.x, 1); p1.y = __shfl_up_sync(0xffffffffu, y1.y, 1);
+        if (lane == 0) { p0 = carry[c]; p1 = carry[c + 1]; }
+        if (kk == k_zero) { p0 = make_float2(0.0f, 0.0f); p1 = make_float2(0.0f, 0.0f); }
+        // arg(conj(prev) y) with separate mul / add like the C reference (A.9)
+        const float re0 = __fadd_rn(__fmul_rn(p0.x, y0.x), __fmul_rn(p0.y, y0.y));
+        const float im0 = __fsub_rn(__fmul_rn(p0.x, y0.y), __fmul_rn(p0.y, y0.x));
+        const float re1 = __fadd_rn(__fmul_rn(p1.x, y1.x), __fmul_rn(p1.y, y1.y));
+        const float im1 = __fsub_rn(__fmul_rn(p1.x, y1.y), __fmul_rn(p1.y, y1.x));
+        const float2 a = fast_atan2f_x2(im0, re0, im1, re1);
+        if (own) {
+          drow0[(long long)c * p.demod_stride + col] = a.x * p.ref;
+          drow0[(long long)(c + 1) * p.demod_stride + col] = a.y * p.ref;
+          if (crow0) {
+            crow0[(long long)c * p.chan_ld + crel + kk] = y0;
+            crow0[(long long)(c + 1) * p.chan_ld + crel + kk] = y1;
+          }
+        }
+        if constexpr (TAPS) {
+          if (own) {
+            ta.macc[c] += sqrtf(fmaf(y0.x, y0.x, y0.y * y0.y));
+            ta.macc[c + 1] += sqrtf(fmaf(y1.x, y1.x, y1.y * y1.y));
+          }
+          if (tp.edge) {
+            float2* e = tp.edge + ((long long)s * 16 + c) * 2;
+            if (own && kk == k_first) { e[0] = y0; e[2] = y1; }
+            if (own && kk == k_last) { e[1] = y0; e[3] = y1; }
+          }
+        }
+      }
+      __syncwarp();   // lane 0 has read the previous batch's last frame
+      if (lane == 31) {
+#pragma unroll
+        for (int c = 0; c < 16; c++) carry[c] = v[af_dig(c)];
+      }
+    }
   }
   if constexpr (TAPS) {
     if (tp.mag_part) {
-      const float m = ta.macc + __shfl_xor_sync(0xffffffffu, ta.macc, 16);
-      if (hsel == 0) tp.mag_part[((long long)s * p.tiles + (warp % p.tiles)) * 16 + br] = m;
+#pragma unroll
+      for (int c = 0; c < 16; c++) {
+        float m = ta.macc[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+        if (lane == 0) tp.mag_part[((long long)s * p.tiles + tile_idx) * 16 + c] = m;
+      }
     }
   }
 }

@@ -1,0 +1,274 @@
+// fused_frontend_kernel: the WHOLE front end of a rate-2/3 plan in one pass, nothing stored in between --
+//   cu8 load -> (u8 - 127.4)/128 -> DC blocker -> half-band m=3 -> m=5 -> m=10 -> 14-tap arbitrary resampler (x 2/3)
+// i.e. iirfilt_crcf_execute_block + msresamp_crcf_execute of the reference for 2.4 Msps input
+// (/root/reference/src/sdr_pmr446.c:795-796), replacing round 1's two launches
+// (cascade_kernel -> 600 kHz ring in HBM -> hbarb_tile_kernel) and their 9.8 GB of ring traffic per 1024-stream step.
+//
+// Same "segment-sequential" mapping as cascade_kernel (frontend.cuh): one thread = one time segment of one stream, run
+// like the CPU does with every filter window in registers -- but
+//  * all samples are (re, im) PAIRS in 64-bit register pairs and every FIR tap is ONE packed FFMA2 (Blackwell's
+//    fma.rn.f32x2) with the tap as a scalar uniform-register operand: half the FMA instructions of the scalar form;
+//  * an iteration is 48 input samples = three 16-sample sub-blocks through DC + the first two half-bands, then 12 samples
+//    at 600 kHz -> 6 at 300 kHz -> 4 resampler outputs (one 32-byte sector, one 256-bit store).  The resampler phase has
+//    period 2 (step = 1.5): outputs 2q, 2q + 1 come from inputs 3q, 3q + 1 with the two filter-bank rows as
+//    constant-bank operands -- no bank gathers, no phase arithmetic;
+//  * raw bytes are prefetched two sub-blocks ahead (16 registers).
+// The DC blocker runs in its zero-state form (DC_ZSR, see frontend.cuh); the zero-input part is added by the consumer of
+// the 200 kHz ring (channelize16_kernel while it stages its tile) or in place by zir_tail_kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <type_traits>
+
+#include "frontend.cuh"
+
+namespace pmr {
+
+// ---- packed FP32 (sm_100: FFMA2 / FADD2 / FMUL2) ---------------------------------------------------------------------
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(*(unsigned long long*)&d) : "l"(*(unsigned long long*)&a), "l"(*(unsigned long long*)&b), "l"(*(unsigned long long*)&c));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(*(unsigned long long*)&d) : "l"(*(unsigned long long*)&a), "l"(*(unsigned long long*)&b));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(*(unsigned long long*)&d) : "l"(*(unsigned long long*)&a), "l"(*(unsigned long long*)&b));
+  return d;
+}
+// scalar tap times a pair: ptxas emits the scalar-broadcast operand form (R.F32 / UR.F32), no duplicate register
+__device__ __forceinline__ float2 fma_tap(float h, float2 x, float2 acc) { return ffma2(make_float2(h, h), x, acc); }
+
+constexpr int FF_THREADS = 128;
+constexpr int FF_SLOTS = 29 + 13;   // shared-memory history per thread: m = 10 stage (19 even + 10 odd) + resampler window (13)
+
+struct FusedParams {
+  CascadeParams c;       // source view, segment grid, DC blocker, destination ring, hb[0..2] = taps of m = 3, 5, 10
+  float arb[2][14];      // filter-bank rows of the two resampler phases, newest first
+};
+
+// one half-band decimator stage on pairs: out[o] = x_odd[o - M] + sum_{j < 2M} h[j] x_even[o - j]   (A.4)
+template <int M, int B, int STAGE>
+struct HbPair {
+  float2 he[2 * M - 1], ho[M];   // previous even / odd samples, oldest first
+  __device__ __forceinline__ void reset() {
+#pragma unroll
+    for (int i = 0; i < 2 * M - 1; i++) he[i] = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int i = 0; i < M; i++) ho[i] = make_float2(0.0f, 0.0f);
+  }
+  // SM: the history lives in the thread's shared-memory column (slot k at sm[k * FF_THREADS]) instead of he / ho, which
+  // are then never touched: a stage that runs once per iteration only needs its window in registers while it runs
+  template <bool SCALE, bool SM = false>
+  __device__ __forceinline__ void run(const CascadeParams& p, const float2* x, float2* y, float scale, float2* sm = nullptr) {
+    float2 e[2 * M - 1 + B], o[M + B];
+#pragma unroll
+    for (int i = 0; i < 2 * M - 1; i++) e[i] = SM ? sm[i * FF_THREADS] : he[i];
+#pragma unroll
+    for (int i = 0; i < M; i++) o[i] = SM ? sm[(2 * M - 1 + i) * FF_THREADS] : ho[i];
+#pragma unroll
+    for (int b = 0; b < B; b++) { e[2 * M - 1 + b] = x[2 * b]; o[M + b] = x[2 * b + 1]; }
+#pragma unroll
+    for (int b = 0; b < B; b++) {
+      float2 acc = o[b];
+#pragma unroll
+      for (int j = 0; j < 2 * M; j++) acc = fma_tap(p.hb[STAGE][j], e[2 * M - 1 + b - j], acc);
+      y[b] = SCALE ? fmul2(acc, make_float2(scale, scale)) : acc;
+    }
+    if (SM) {
+#pragma unroll
+      for (int i = 0; i < 2 * M - 1; i++) sm[i * FF_THREADS] = e[B + i];
+#pragma unroll
+      for (int i = 0; i < M; i++) sm[(2 * M - 1 + i) * FF_THREADS] = o[B + i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 2 * M - 1; i++) he[i] = e[B + i];
+#pragma unroll
+      for (int i = 0; i < M; i++) ho[i] = o[B + i];
+    }
+  }
+};
+
+// cu8 -> pair, exactly fl((u8 - fl(127.4)) / 128) like the scalar loader: PRMT drops the byte into the mantissa of 2^23,
+// one packed FADD removes the 2^23, one packed FFMA scales and offsets
+__device__ __forceinline__ float2 cu8_pair(unsigned w, int k) {
+  const float2 raw = make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + (unsigned)(2 * k))),
+                                 __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + (unsigned)(2 * k + 1))));
+  const float2 u = fadd2(raw, make_float2(-8388608.0f, -8388608.0f));
+  return ffma2(u, make_float2(1.0f / 128.0f, 1.0f / 128.0f), make_float2(-127.4f / 128.0f, -127.4f / 128.0f));
+}
+
+constexpr int FF_G = 48;        // input samples per iteration
+constexpr int FF_SUB = 16;      // ... in three sub-blocks of 16 (32 bytes of cu8)
+constexpr int FF_D = 8;         // decimation of the three half-bands
+constexpr int FF_NO = 4;        // resampler outputs per iteration
+constexpr int FF_PF = 8;        // L1 prefetch distance in sub-blocks
+
+__device__ __forceinline__ void ldg256_nc(const void* p, unsigned* w) {
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
+}
+
+// SMH = false (shipped): every history in registers, ~250 registers, 2 blocks per SM.  SMH = true: the histories of the two
+// stages that run once per iteration (m = 10 half-band, resampler) live in shared memory (42 slots x 128 threads x 8 B =
+// 43 KB, thread-private columns: a warp's access to one slot is 256 contiguous bytes), 167 registers, 3 blocks per SM --
+// measured 2.75 ms against 2.68 ms (1024 streams), so occupancy is not what limits this kernel.
+template <int DC, int NB = 2, bool SMH = false>
+__global__ void __launch_bounds__(FF_THREADS, NB) fused_frontend_kernel(FusedParams fp) {
+  __shared__ float2 ff_hist[SMH ? FF_SLOTS * FF_THREADS : 1];
+  float2* const smc = ff_hist + (SMH ? threadIdx.x : 0);
+  float2* const sma = smc + (SMH ? 29 * FF_THREADS : 0);
+  if (SMH) {
+#pragma unroll
+    for (int i = 0; i < FF_SLOTS; i++) smc[i * FF_THREADS] = make_float2(0.0f, 0.0f);
+  }
+  const CascadeParams& p = fp.c;
+  long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)p.n_streams * p.nseg) return;
+  const int s = (int)(gid / p.nseg), t = (int)(gid % p.nseg);
+  const long long T0 = p.seg0 + (long long)t * p.seg_len;
+  long long i_lo = T0 / FF_D, i_hi = (T0 + p.seg_len) / FF_D;     // owned 300 kHz samples
+  if (i_lo < p.out0) i_lo = p.out0;
+  if (i_hi > p.out1) i_hi = p.out1;
+  long long qb = T0 - p.halo;
+  long long q_cap = qb + p.seg_len;                               // where this segment's local DC sum is complete
+  if (DC == DC_ZSR && q_cap > p.dc_end) q_cap = p.dc_end;
+  if (qb < 0) qb = 0;
+  long long q_end = i_hi > i_lo ? i_hi * FF_D : qb;
+  if (DC == DC_ZSR && q_cap > q_end) q_end = q_cap;
+  if (q_end <= qb) {
+    if (DC == DC_ZSR) p.sums[gid] = make_float2(0.0f, 0.0f);
+    return;
+  }
+  // everything below is 32-bit and relative to qb (a multiple of 48: every iteration starts at resampler phase 0)
+  const int n_it = (int)((q_end - qb + FF_G - 1) / FF_G);
+  const int cap_it = (DC == DC_ZSR) ? (q_cap > qb ? (int)((q_cap - qb) / FF_G) : 0) : -1;
+  const long long ob = qb / FF_D;                                  // absolute 300 kHz index of local sample 0
+  int own_lo = (int)(i_lo - ob), own_hi = (int)(i_hi - ob);
+  if (i_hi <= i_lo) own_lo = own_hi = 0;
+
+  HbPair<3, FF_SUB / 2, 0> sa;
+  HbPair<5, FF_SUB / 4, 1> sb;
+  HbPair<10, FF_G / 8, 2> sc;
+  sa.reset(); sb.reset(); sc.reset();
+  float2 aw[13];                                                   // resampler window: previous 300 kHz samples, oldest first
+#pragma unroll
+  for (int i = 0; i < 13; i++) aw[i] = make_float2(0.0f, 0.0f);
+  float2 v = make_float2(0.0f, 0.0f);                              // DC blocker state (zero-state response)
+
+  float2* dst = p.dst + (long long)s * p.dst_stride;
+  const unsigned dmask = (unsigned)p.dst_mask;
+  const unsigned jb32 = (unsigned)(qb / 12);                       // ring index of local resampler output 0 (multiple of 4)
+  const float scale = p.scale;
+  const float2 nalpha = make_float2(-p.alpha, -p.alpha);
+
+  Loader<SRC_CU8> ld;
+  ld.template init<FF_SUB>(p.src, s, qb);
+  const int n_sub = 3 * n_it;
+  Raw<SRC_CU8, FF_SUB> raw[3];
+  // Loads go through L1 here (unlike cascade_kernel's no-allocate loads): with ~250 registers per thread ptxas sinks the
+  // register loads towards their use, so the DRAM latency is taken by a register-free L1 prefetch issued FF_PF
+  // sub-blocks ahead and the load proper, two sub-blocks ahead, hits L1.  256 threads x 8 sectors in flight = 64 KB of L1.
+  auto fetch = [&](int sbi, Raw<SRC_CU8, FF_SUB>& r) {
+    if (sbi >= ld.fast_lo && sbi < ld.fast_hi) ldg256_nc(ld.fp + (size_t)sbi * (2 * FF_SUB), r.w);
+  };
+  auto prefetch = [&](int sbi) {
+    if (sbi >= ld.fast_lo && sbi < ld.fast_hi) asm volatile("prefetch.global.L1 [%0];" ::"l"(ld.fp + (size_t)sbi * (2 * FF_SUB)));
+  };
+#pragma unroll
+  for (int i = 2; i < FF_PF; i++) prefetch(i);
+  fetch(0, raw[0]);
+  if (n_sub > 1) fetch(1, raw[1]);
+  const float2 cpole = make_float2(1.0f - p.alpha, 1.0f - p.alpha);   // exact: alpha is 1 - fl(1 - alpha_nominal)
+
+  // One iteration = 48 input samples.  FAST: all three sub-blocks are whole aligned 32-byte groups of the current chunk --
+  // straight-line code (one basic block, so the scheduler overlaps the DC recurrence of one sub-block with the FIR work
+  // of another); otherwise the guarded per-sample loader fills the same registers.
+  auto iteration = [&](const int it, auto fast_tag) {
+    constexpr bool FAST = decltype(fast_tag)::value;
+    float2 cin[12];                                                // 600 kHz samples of this iteration
+#pragma unroll
+    for (int sub = 0; sub < 3; sub++) {
+      const int sbi = 3 * it + sub;
+      if (sbi + FF_PF < n_sub) prefetch(sbi + FF_PF);
+      if (sbi + 2 < n_sub) fetch(sbi + 2, raw[(sub + 2) % 3]);   // two sub-blocks ahead
+      float2 x[FF_SUB];
+      if (FAST) {
+#pragma unroll
+        for (int j = 0; j < FF_SUB / 2; j++) { x[2 * j] = cu8_pair(raw[sub].w[j], 0); x[2 * j + 1] = cu8_pair(raw[sub].w[j], 1); }
+      } else {
+        float xr[FF_SUB], xi[FF_SUB];
+        ld.template convert<FF_SUB>(p.src, qb + (long long)sbi * FF_SUB, sbi, raw[sub], xr, xi);
+#pragma unroll
+        for (int i = 0; i < FF_SUB; i++) x[i] = make_float2(xr[i], xi[i]);
+      }
+      if (DC != DC_NONE) {
+        // A.1 dc blocker, zero-state part: y = x - alpha v[n-1], v[n] = (1 - alpha) v[n-1] + x.  Only the one-FFMA2
+        // recurrence of v is serial; the outputs hang off it.
+#pragma unroll
+        for (int i = 0; i < FF_SUB; i++) {
+          const float2 y = ffma2(nalpha, v, x[i]);
+          v = ffma2(cpole, v, x[i]);
+          x[i] = y;
+        }
+      }
+      float2 a[FF_SUB / 2], b[FF_SUB / 4];
+      sa.template run<false>(p, x, a, 1.0f);
+      sb.template run<false>(p, a, b, 1.0f);
+#pragma unroll
+      for (int i = 0; i < 4; i++) cin[4 * sub + i] = b[i];
+    }
+    float2 c[6];                                                   // 300 kHz, scaled by 2^-3 like msresamp2 does
+    sc.template run<true, SMH>(p, cin, c, scale, smc);
+    // arbitrary resampler (A.5), phase period 2: outputs 4 it + {0, 1, 2, 3} sit at local inputs 6 it + {0, 1, 3, 4}
+    float2 w[13 + 6];
+#pragma unroll
+    for (int i = 0; i < 13; i++) w[i] = SMH ? sma[i * FF_THREADS] : aw[i];
+#pragma unroll
+    for (int i = 0; i < 6; i++) w[13 + i] = c[i];
+    float2 o[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int io = 3 * (r / 2) + (r % 2);
+      float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll
+      for (int k = 0; k < 14; k++) acc = fma_tap(fp.arb[r % 2][k], w[13 + io - k], acc);
+      o[r] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < 13; i++) {
+      if (SMH) sma[i * FF_THREADS] = w[6 + i];
+      else aw[i] = w[6 + i];
+    }
+
+    const int lo = own_lo - 6 * it, hi = own_hi - 6 * it;          // owned local inputs of this iteration are [lo, hi)
+    float2* d4 = dst + ((jb32 + 4u * (unsigned)it) & dmask);       // 32-byte aligned, never straddles the ring's end
+    if (lo <= 0 && hi >= 5) {
+      const float f[8] = {o[0].x, o[0].y, o[1].x, o[1].y, o[2].x, o[2].y, o[3].x, o[3].y};
+      stg256(d4, f);
+    } else if (hi > 0 && lo < 5) {
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const int io = 3 * (r / 2) + (r % 2);
+        if (io >= lo && io < hi) d4[r] = o[r];
+      }
+    }
+  };
+  for (int it = 0; it < n_it; it++) {
+    if (DC == DC_ZSR) {
+      if (it == cap_it) p.sums[gid] = v;
+    }
+    if (3 * it >= ld.fast_lo && 3 * it + 2 < ld.fast_hi) iteration(it, std::true_type());
+    else iteration(it, std::false_type());
+  }
+  if (DC == DC_ZSR) {
+    if (cap_it >= n_it) p.sums[gid] = v;
+  }
+}
+
+}  // namespace pmr

@@ -12,6 +12,7 @@
 #include "common_host.hpp"
 #include "design.hpp"
 #include "frontend.cuh"
+#include "frontend_fused.cuh"
 #include "hbarb_tile.cuh"
 
 namespace pmr {
@@ -30,6 +31,7 @@ struct Level {
   float scale = 1.0f;
   cascade_fn fn = nullptr;
   bool tile = false;      // last level runs hbarb_tile_kernel<10, 2, 3> instead of the segment-sequential cascade
+  bool fused = false;     // the only level: fused_frontend_kernel (cu8 -> m = 3, 5, 10 -> resampler x 2/3) in one pass
   float arb_rows[2][14];
   DevBuf ring;            // output ring [S][cap] float2
   long long cap = 0;
@@ -97,6 +99,11 @@ struct Frontend {
   struct OutView { void* p; } out;   // final ring (levels.back())
   long long out_cap = 0, n_out = 0;
   unsigned max_chunk = 0;
+  // A fused level leaves the DC blocker's zero-input part of the samples [pending.from, n_out) of the OUT ring to its
+  // consumer (see execute(defer_zir)); tail_fix = how much history the ring keeps for the next call
+  Correction pending;
+  bool has_pending = false;
+  long long tail_fix = 0;
 
   long long max_out_per_chunk() const { return levels.empty() ? 0 : levels.back().max_out; }
   // resampler outputs that exist once n_total raw samples have been consumed (closed form, A.2/A.5): lets the callers
@@ -125,8 +132,21 @@ struct Frontend {
       }
       x.swap(y);
     }
+    for (auto& xv : x) xv *= (double)L.scale;
+    if (L.fused) {   // ... followed by the arbitrary resampler (A.5): output j sits at input (j step) >> 24
+      std::vector<double> y;
+      for (uint64_t j = 0;; j++) {
+        const uint64_t ph = j * (uint64_t)plan.step, pos = ph >> 24;
+        if (pos >= x.size()) break;
+        const unsigned row = (unsigned)((ph & ((1u << 24) - 1)) >> (24 - plan.bits));
+        double acc = 0.0;
+        for (unsigned k = 0; k < plan.sub_len && k <= pos; k++) acc += (double)plan.pfb[(size_t)row * plan.sub_len + k] * x[pos - k];
+        y.push_back(acc);
+      }
+      x.swap(y);
+    }
     std::vector<float> e(x.size());
-    for (size_t i = 0; i < x.size(); i++) e[i] = (float)(x[i] * (double)L.scale);
+    for (size_t i = 0; i < x.size(); i++) e[i] = (float)x[i];
     return e;
   }
 
@@ -156,16 +176,26 @@ struct Frontend {
     // the lowest rate (half the traffic) and the per-lane filter-bank gathers no longer share a kernel with the 58-register
     // m = 10 window.  Otherwise the last half-band goes with the resampler (tiled kernel when the phase has period 2).
     const bool split_arb = order.size() == 2 && order[0] == 5 && order[1] == 10 && plan.step != (3u << 23);
-    if (!order.empty() && !split_arb) { last.push_back(order.back()); order.pop_back(); }
-    for (size_t i = 0; i < order.size(); i += 4) groups.emplace_back(order.begin() + i, order.begin() + std::min(order.size(), i + 4));
-    groups.push_back(last);   // may be empty (rate >= 0.5)
+    // 2.4 Msps cu8 -> 200 kHz ([3, 5, 10] + rate 2/3): everything in ONE launch, no intermediate ring (frontend_fused.cuh).
+    // PMR446_FRONTEND=split keeps round 1's two launches (cascade -> 600 kHz ring -> tiled half-band + resampler) for A/B runs.
+    const char* fe_env = getenv("PMR446_FRONTEND");
+    const bool want_fused = in_fmt == PMR446_FMT_CU8 && order.size() == 3 && order[0] == 3 && order[1] == 5 && order[2] == 10 &&
+                            plan.step == (3u << 23) && !(fe_env && strcmp(fe_env, "split") == 0);
+    if (want_fused) {
+      groups.push_back(order);
+    } else {
+      if (!order.empty() && !split_arb) { last.push_back(order.back()); order.pop_back(); }
+      for (size_t i = 0; i < order.size(); i += 4) groups.emplace_back(order.begin() + i, order.begin() + std::min(order.size(), i + 4));
+      groups.push_back(last);   // may be empty (rate >= 0.5)
+    }
     levels.resize(groups.size());
     long long max_in = max_chunk;
     int stage_cursor = (int)plan.stages - 1;  // index into plan.m / plan.hb of the next stage to place
     for (size_t l = 0; l < groups.size(); l++) {
       Level& L = levels[l];
       L.src = (l == 0) ? (in_fmt == PMR446_FMT_CU8 ? SRC_CU8 : SRC_CF32) : SRC_RING;
-      L.dc = (l == 0 && dc) ? (groups.size() >= 2 ? DC_ZSR : DC_SCAN) : DC_NONE;
+      L.fused = want_fused;
+      L.dc = (l == 0 && dc) ? ((groups.size() >= 2 || L.fused) ? DC_ZSR : DC_SCAN) : DC_NONE;
       L.arb = (l + 1 == groups.size());
       L.nst = (int)groups[l].size();
       L.D = 1 << L.nst;
@@ -180,8 +210,8 @@ struct Frontend {
       }
       if (L.arb) halo += 14 * L.D;
       L.scale = 1.0f / (float)L.D;
-      L.fn = pick_cascade(L.src, L.dc, L.arb, L.ms, &L.G);
-      if (!L.fn) {
+      if (!L.fused) L.fn = pick_cascade(L.src, L.dc, L.arb, L.ms, &L.G);
+      if (!L.fn && !L.fused) {
         char msg[160];
         snprintf(msg, sizeof msg, "resampler plan not built: level %zu src=%d dc=%d arb=%d stages=[%d,%d,%d,%d]", l, L.src, L.dc,
                  (int)L.arb, L.ms[0], L.ms[1], L.ms[2], L.ms[3]);
@@ -198,7 +228,21 @@ struct Frontend {
       while (seg_min < 4 * L.halo || seg_min < L.unit) seg_min <<= 1;
       while (seg > seg_min && (long long)S * ((max_in + seg - 1) / seg) < 148LL * 1024) seg >>= 1;
       L.seg_len = std::max(seg, seg_min);
-      if (L.arb) {
+      if (L.fused) {
+        // every segment starts at resampler phase 0 on a 48-sample grid and holds 2^k resampler outputs (the consumer
+        // finds its producer segment with a shift): seg_len = 12 * 2^k
+        L.G = FF_G;
+        L.unit = FF_G;
+        L.halo = (halo + L.D + FF_G - 1) / FF_G * FF_G;
+        int sl = 6144;
+        while (sl > 1536 && (long long)S * ((max_in + sl - 1) / sl) < 148LL * 256) sl >>= 1;
+        L.seg_len = sl;
+        for (int r = 0; r < 2; r++) {
+          const unsigned row = (unsigned)((((unsigned long long)r * plan.step) & ((1u << 24) - 1)) >> (24 - plan.bits));
+          for (int k = 0; k < 14; k++) L.arb_rows[r][k] = plan.pfb[(size_t)row * plan.sub_len + k];
+        }
+      }
+      if (L.arb && !L.fused) {
         // equal resampler phase at every segment start (all lanes of a warp then emit outputs in
         // lock-step) needs (seg_len / D) * 2^24 = 0 mod step
         unsigned long long g = plan.step, b = 1ull << 24;
@@ -247,6 +291,7 @@ struct Frontend {
     if (int rc = v_lag.alloc_zero((size_t)S * sizeof(float2))) return rc;
     if (int rc = sums.alloc_zero((size_t)S * max_seg0 * sizeof(float2))) return rc;
     if (int rc = v_seg.alloc_zero((size_t)S * max_seg0 * sizeof(float2))) return rc;
+    tail_fix = extra_hist;
     if (L0.dc == DC_ZSR) {
       std::vector<float> e = zir_table(L0);
       if (int rc = e_table.alloc((e.size() + 16) * sizeof(float))) return rc;
@@ -277,8 +322,23 @@ struct Frontend {
 
   // Consumes n raw samples per stream ([n_in, n_in + n)); afterwards n_out is the absolute
   // number of output samples in the `out` ring.
-  int execute(const void* iq, long long iq_stride, unsigned n, cudaStream_t st, int* launches, Timer* tm = nullptr) {
+  // defer_zir: the caller's consumer applies pending_corr() while it reads the ring and then calls fix_pending(false);
+  // otherwise execute() finishes the ring itself (one extra read-modify-write pass over the new samples).
+  const Correction* pending_corr() const { return has_pending ? &pending : nullptr; }
+  void fix_pending(cudaStream_t st, int* launches, bool all, Timer* tm = nullptr) {
+    if (!has_pending) return;
+    has_pending = false;
+    const Level& L = levels.back();
+    const long long start = all ? pending.from : std::max(pending.from, L.n_out - tail_fix), count = L.n_out - start;
+    if (count <= 0) return;
+    zir_tail_kernel<<<dim3((unsigned)((count + 127) / 128), S), 128, 0, st>>>((float2*)L.ring.p, L.cap, L.cap - 1, pending, start, (int)count);
+    *launches += 1;
+    if (tm) tm->mark(st, TM_HIST);
+  }
+
+  int execute(const void* iq, long long iq_stride, unsigned n, cudaStream_t st, int* launches, Timer* tm = nullptr, bool defer_zir = false) {
     const long long n0 = n_in, n1 = n_in + n;
+    has_pending = false;
     Timer dummy;
     if (!tm) tm = &dummy;
     SrcView v0;
@@ -375,6 +435,36 @@ struct Frontend {
           tm->mark(st, TM_CASCADE0 + (int)std::min<size_t>(l, 2));
           new_out = j1;
         }
+      } else if (L.fused) {
+        if (out1 > out0 || (L.dc == DC_ZSR && nseg > 0)) {
+          FusedParams fp;
+          memset(&fp, 0, sizeof fp);
+          CascadeParams& cp = fp.c;
+          cp.src = sv;
+          cp.n_streams = S;
+          cp.nseg = nseg;
+          cp.seg0 = seg0;
+          cp.seg_len = L.seg_len;
+          cp.halo = L.halo;
+          cp.out0 = out0;
+          cp.out1 = out1;
+          cp.scale = L.scale;
+          cp.alpha = alpha_eff;
+          cp.sums = (float2*)sums.p;
+          cp.dc_end = seg0_next - L.halo;
+          cp.dst = (float2*)L.ring.p;
+          cp.dst_stride = L.cap;
+          cp.dst_mask = L.cap - 1;
+          memcpy(cp.hb, L.hb, sizeof cp.hb);
+          memcpy(fp.arb, L.arb_rows, sizeof fp.arb);
+          static const bool smem3 = getenv("PMR446_FF_VARIANT") && strcmp(getenv("PMR446_FF_VARIANT"), "smem3") == 0;   // tuning probe
+          if (L.dc != DC_ZSR) fused_frontend_kernel<DC_NONE><<<blocks, FF_THREADS, 0, st>>>(fp);
+          else if (smem3) fused_frontend_kernel<DC_ZSR, 3, true><<<blocks, FF_THREADS, 0, st>>>(fp);
+          else fused_frontend_kernel<DC_ZSR><<<blocks, FF_THREADS, 0, st>>>(fp);
+          *launches += 1;
+          tm->mark(st, TM_CASCADE0);
+          if (out1 > out0) new_out = (long long)design::arb_outputs_after((uint64_t)out1, plan.step);
+        }
       } else if (out1 > out0 || (L.dc == DC_ZSR && nseg > 0)) {
         CascadeParams cp;
         memset(&cp, 0, sizeof cp);
@@ -407,14 +497,16 @@ struct Frontend {
         dc_scan_kernel<<<(unsigned)(((long long)S * 32 + 127) / 128), 128, 0, st>>>(sp);
         *launches += 1;
         tm->mark(st, TM_DC);
+        // ring samples per input sample of this level: 1 / D, or 1 / 12 with the x 2/3 resampler fused in
+        const int per_out = L.fused ? 12 : L.D;
         int shift = 0;
-        while ((1 << shift) < L.seg_len / L.D) shift++;
+        while ((1 << shift) < L.seg_len / per_out) shift++;
         corr.v_seg = (const float2*)v_seg.p;
         corr.e = (const float*)e_table.p;
-        corr.from = out0;
-        corr.seg0_out = seg0 / L.D;
+        corr.from = L.fused ? L.n_out : out0;
+        corr.seg0_out = seg0 / per_out;
         corr.seg_shift = shift;
-        corr.halo_out = L.halo / L.D;
+        corr.halo_out = L.halo / per_out;
         corr.nseg = nseg;
         corr.alpha = alpha_eff;
         for (int i = 0; i < 16; i++) corr.rho_pow[i] = (float)pow((double)c_pole, (double)(i * L.D));
@@ -455,6 +547,11 @@ struct Frontend {
     }
     n_in = n1;
     n_out = levels.back().n_out;
+    if (corr.v_seg) {   // set by the LAST level: only a fused level does that
+      pending = corr;
+      has_pending = true;
+      if (!defer_zir) fix_pending(st, launches, true, tm);
+    }
     return 0;
   }
 };

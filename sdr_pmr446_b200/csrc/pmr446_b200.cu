@@ -122,7 +122,8 @@ extern "C" int pmr446_batch_create(const pmr446_config* cfg, pmr446_batch** out)
 
   float fs_res = (float)(cfg->num_channels * cfg->channel_width);
   int rc = b->fe.init(S, cfg->in_fmt, fs_res / (float)cfg->fs_in, cfg->resamp_as, true, cfg->dc_alpha, cfg->max_chunk,
-                      /*extra_hist=*/std::max<long long>((long long)M * (2 * cfg->pfb_m + CG_FT + 4), (long long)cfg->waterfall) + 64);
+                      /*extra_hist=*/std::max<long long>(std::max<long long>((long long)M * (2 * cfg->pfb_m + CG_FT + 4), (long long)cfg->waterfall),
+                                                         16LL * (CH_FR + CH_HIST + 2)) + 64);   // a call recomputes at most one channelizer tile
   if (rc) { pmr446_batch_destroy(b); return rc; }
   b->max_res = b->fe.max_out_per_chunk();
   b->max_ns = b->max_res / M + 1;
@@ -358,7 +359,12 @@ extern "C" int pmr446_batch_execute_device(pmr446_batch* b, const void* iq, long
   // ---- front end: [r0, r1) new resampler outputs in fe.out ring ------------------------------
   long long r0 = b->fe.n_out, r1 = 0;
   b->timer.mark(st, TM_START);
-  int rc = b->fe.execute(iq, iq_stride, n, st, &b->launches, &b->timer);
+  // The fused front end leaves the zero-input part of its DC blocker to the consumer of the ring.  channelize16_kernel
+  // adds it while staging its tiles; if anything else reads the new samples (res output, generic channelizer, waterfall)
+  // the ring is finished in place first (one read-modify-write pass over the chunk).
+  const bool want_wf_now = b->cfg.waterfall > 0 && (out->ascii || out->peak || out->psd);
+  const bool defer_zir = !b->generic && !out->res && !want_wf_now;
+  int rc = b->fe.execute(iq, iq_stride, n, st, &b->launches, &b->timer, defer_zir);
   if (rc) return rc;
   r1 = b->fe.n_out;
   const long long ny = r1 - r0;
@@ -425,6 +431,8 @@ extern "C" int pmr446_batch_execute_device(pmr446_batch* b, const void* iq, long
     cp.demod_mask = b->demod_cap - 1;
     cp.chan = (float2*)out->chan;
     cp.chan_ld = out->ld;
+    memset(&cp.corr, 0, sizeof cp.corr);
+    if (const Correction* pc = b->fe.pending_corr()) cp.corr = *pc;
     ChanTaps tp;
     tp.mag_part = out->rssi ? (float*)b->d_mag.p : nullptr;
     tp.edge = (float2*)out->chan_edge;
@@ -442,10 +450,12 @@ extern "C" int pmr446_batch_execute_device(pmr446_batch* b, const void* iq, long
       b->launches++;
     }
     b->timer.mark(st, TM_CHANNELIZE);
+    b->fe.fix_pending(st, &b->launches, false, &b->timer);   // the ring's tail is the next call's history: finish it in place
   } else if (out->rssi) {   // empty window: 0 / 0 like the reference's average_power()
     rssi_finalize_kernel<<<(S * 16 + 127) / 128, 128, 0, st>>>((const float*)b->d_mag.p, 0, S * 16, 0, out->rssi);
     b->launches++;
   }
+  b->fe.fix_pending(st, &b->launches, true, &b->timer);      // no channelizer launch in this call (ns == 0): nothing was deferred to
   if (ns > 0) {
     if (out->demod) {
       gather_ring_kernel<float><<<dim3((unsigned)((ns + 255) / 256), S * M), 256, 0, st>>>((const float*)b->d_demod.p, b->demod_cap,
