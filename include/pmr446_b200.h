@@ -238,6 +238,10 @@ int pmr446_design_pfbch(unsigned M, unsigned m, float as, float *taps);
 int pmr446_design_asgram_window(unsigned W, float *w);
 /* nco_crcf_set_frequency(dtheta) as a 32-bit phase increment. */
 unsigned pmr446_design_nco_dtheta(float dtheta);
+/* How msresamp_crcf_create(rate, as) (src/sdr_pmr446.c:425-426, src/dsd_in.c:100) is cut into kernel launches for the
+ * given input format, e.g. "fused[3,5,10]+arb" or "cascade[3,3,3,3] | cascade[3,5] | tile[10]+arb"; every decimating
+ * rate liquid accepts (0 < rate <= 1) has a plan.  buf receives the NUL-terminated description. */
+int pmr446_describe_frontend(float rate, float as, int in_fmt, int with_dc, char *buf, int len);
 /* Total msresamp outputs after n_in inputs since stream start (decimating rates). */
 long long pmr446_count_resampled(float rate, float as, long long n_in);
 

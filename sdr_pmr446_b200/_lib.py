@@ -75,7 +75,7 @@ EXPORTS = [
     "dsd446_default_config", "dsd446_batch_create", "dsd446_batch_destroy", "dsd446_batch_max_res",
     "dsd446_batch_max_out", "dsd446_batch_execute", "dsd446_batch_execute_device", "dsd446_batch_reset",
     "pmr446_design_msresamp", "pmr446_design_pfbch", "pmr446_design_asgram_window", "pmr446_design_nco_dtheta",
-    "pmr446_count_resampled",
+    "pmr446_count_resampled", "pmr446_describe_frontend",
 ]
 
 
@@ -148,6 +148,7 @@ def lib():
         L.pmr446_design_nco_dtheta.restype = C.c_uint
         L.pmr446_count_resampled.argtypes = [C.c_float, C.c_float, C.c_longlong]
         L.pmr446_count_resampled.restype = C.c_longlong
+        L.pmr446_describe_frontend.argtypes = [C.c_float, C.c_float, C.c_int, C.c_int, C.c_char_p, C.c_int]
         _LIB = L
     return _LIB
 

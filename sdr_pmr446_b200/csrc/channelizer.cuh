@@ -106,13 +106,33 @@ __device__ __forceinline__ float2 fast_atan2f_x2(float y0, float x0, float y1, f
   return make_float2(copysignf(r.x, y0), copysignf(r.y, y1));
 }
 
+// forward 16-point DFT like dft16<false> (audio_fft.cuh; output q ends in v[af_dig(q)]) with the plain complex
+// additions as packed FADD2: 6 packed + 4 scalar instructions per radix-4 butterfly instead of 16 scalar ones
+__device__ __forceinline__ void dft4p(float2& a, float2& b, float2& c, float2& d) {
+  const float2 s0 = fadd2(a, c), s2 = fadd2(b, d);
+  const float2 s1 = fadd2(a, make_float2(-c.x, -c.y)), s3 = fadd2(b, make_float2(-d.x, -d.y));
+  a = fadd2(s0, s2);
+  c = fadd2(s0, make_float2(-s2.x, -s2.y));
+  b = make_float2(s1.x + s3.y, s1.y - s3.x);
+  d = make_float2(s1.x - s3.y, s1.y + s3.x);
+}
+__device__ __forceinline__ void dft16p(float2* v) {
+#pragma unroll
+  for (int m0 = 0; m0 < 4; m0++) dft4p(v[m0], v[m0 + 4], v[m0 + 8], v[m0 + 12]);
+  rot16<1, false>(v[5]);  rot16<2, false>(v[9]);   rot16<3, false>(v[13]);
+  rot16<2, false>(v[6]);  rot16<4, false>(v[10]);  rot16<6, false>(v[14]);
+  rot16<3, false>(v[7]);  rot16<6, false>(v[11]);  rot16<9, false>(v[15]);
+#pragma unroll
+  for (int q1 = 0; q1 < 4; q1++) dft4p(v[4 * q1], v[4 * q1 + 1], v[4 * q1 + 2], v[4 * q1 + 3]);
+}
+
 template <bool TAPS> struct TapState { float macc[16]; };
 template <> struct TapState<false> {};
 
 // TAPS = the selector taps (mag_part / edge) are wanted: a separate instantiation, so that the throughput path carries
 // none of their registers.
 template <bool NCO_CONST, bool TAPS>
-__global__ void __launch_bounds__(128, 4) channelize16_kernel(ChanParams p, ChanTaps tp) {
+__global__ void __launch_bounds__(128, 3) channelize16_kernel(ChanParams p, ChanTaps tp) {
   __shared__ __align__(16) float2 ch_smem[4 * CH_SMEM_WARP];
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -209,13 +229,71 @@ __global__ void __launch_bounds__(128, 4) channelize16_kernel(ChanParams p, Chan
   // with the frame before the first owned frame, the last one the one with the last owned frame
   const bool any = own_hi > own_lo;             // (every launched tile owns a frame; kept warp-uniform and safe anyway)
   const int b_first = any ? (own_lo - 1) / 32 : 0, b_last = any ? (own_hi - 1) / 32 : -1;
-  if (any)
-    for (int pp = 2 * lane; pp < CH_HIST * 16; pp += 64) stage_pair(pp, 512 * b_first, 0);   // history of the first batch
+
   if (lane < 16) carry[lane] = make_float2(0.0f, 0.0f);
+
+  // steady-state staging (warp-uniform per batch): every new sample of the batch exists and they all take the same
+  // correction path.  Then the batch's eight 128-bit loads per lane are issued one batch AHEAD -- after phase A of the
+  // previous batch, when its 33-sample window is dead -- and sit in registers across phase B + C.
+  auto steady = [&](int b, bool& corr_all) {
+    const int jb = 512 * b + CH_HIST * 16, rel_b = seg_rel0 + jb;
+    corr_all = vrow && jb >= from_rel && rel_b >= 0 && ((rel_b + 511) >> cr.seg_shift) < cr.nseg;
+    const bool corr_none = !vrow || jb + 512 <= from_rel;
+    return NCO_CONST && jb >= lo_rel && jb + 512 <= hi_rel && (corr_all || corr_none);
+  };
+  // history of the first batch, steady state: all seven 128-bit loads per lane in flight at once (the guarded
+  // stage_pair loop below takes one DRAM round trip per pair)
+  auto stage_history_fast = [&](int b) {
+    const int jb = 512 * b, rel_b = seg_rel0 + jb;
+    constexpr int NP = (CH_HIST * 16 / 2 + 31) / 32;   // 7, the last one partial
+    const bool corr_all = vrow && jb >= from_rel && rel_b >= 0 && ((rel_b + CH_HIST * 16 - 1) >> cr.seg_shift) < cr.nseg;
+    const bool corr_none = !vrow || jb + CH_HIST * 16 <= from_rel;
+    if (!(NCO_CONST && jb >= lo_rel && jb + CH_HIST * 16 <= hi_rel && (corr_all || corr_none))) return false;
+    float4 hv[NP];
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+      const int pp = 2 * lane + 64 * i;
+      hv[i] = pp < CH_HIST * 16 ? *(const float4*)(res + ((j0_32 + (unsigned)(jb + pp)) & rmask)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    if (corr_all) {
+#pragma unroll
+      for (int i = 0; i < NP; i++) {
+        const int pp = 2 * lane + 64 * i;
+        if (pp < CH_HIST * 16) {
+          const unsigned rel = (unsigned)(rel_b + pp);
+          const float2 v0 = vrow[rel >> cr.seg_shift];
+          const float2 e = *(const float2*)(cr.e + cr.halo_out + (rel & smask));
+          const float ax = nalpha * v0.x, ay = nalpha * v0.y;
+          hv[i] = make_float4(fmaf(ax, e.x, hv[i].x), fmaf(ay, e.x, hv[i].y), fmaf(ax, e.y, hv[i].z), fmaf(ay, e.y, hv[i].w));
+        }
+      }
+    }
+    const float c0 = pcs[0][0], s0 = psn[0][0], c1 = pcs[0][1], s1 = psn[0][1];
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+      const int pp = 2 * lane + 64 * i;
+      if (pp < CH_HIST * 16)
+        *(float4*)(X + pp) = make_float4(fmaf(hv[i].x, c0, hv[i].y * s0), fmaf(hv[i].y, c0, -hv[i].x * s0),
+                                         fmaf(hv[i].z, c1, hv[i].w * s1), fmaf(hv[i].w, c1, -hv[i].z * s1));
+    }
+    return true;
+  };
+  float4 t[8];
+  auto issue_loads = [&](int b) {
+    const int jb = 512 * b + CH_HIST * 16;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t[i] = *(const float4*)(res + ((j0_32 + (unsigned)(jb + 2 * lane + 64 * i)) & rmask));
+  };
+  bool ca_next = false;
+  bool fast_next = any && steady(b_first, ca_next);
+  if (fast_next) issue_loads(b_first);
+  if (any && !stage_history_fast(b_first))
+    for (int pp = 2 * lane; pp < CH_HIST * 16; pp += 64) stage_pair(pp, 512 * b_first, 0);   // history of the first batch
 
 #pragma unroll 1
   for (int batch = b_first; batch <= b_last; batch++) {
     const int boff = 512 * batch;
+    const bool fast = fast_next, corr_all = ca_next;
     if (batch > b_first) {   // the last 25 frames of the previous batch become this batch's history
       __syncwarp();
       constexpr int NC = (CH_HIST * 16 / 2 + 31) / 32;   // float4 copies per lane: 200 in all
@@ -233,8 +311,31 @@ __global__ void __launch_bounds__(128, 4) channelize16_kernel(ChanParams p, Chan
       }
     }
     // ---- staging: 32 new frames = 512 samples, 8 pairs per lane --------------------------------------------------------------
+    if (fast) {
+      if (corr_all) {
+        const int rel_b = seg_rel0 + boff + CH_HIST * 16;
+        float2 v0[8], e[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) stage_pair(CH_HIST * 16 + 2 * lane + 64 * i, boff, 1);
+        for (int i = 0; i < 8; i++) {
+          const unsigned rel = (unsigned)(rel_b + 2 * lane + 64 * i);
+          v0[i] = vrow[rel >> cr.seg_shift];
+          e[i] = *(const float2*)(cr.e + cr.halo_out + (rel & smask));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const float ax = nalpha * v0[i].x, ay = nalpha * v0[i].y;
+          t[i] = make_float4(fmaf(ax, e[i].x, t[i].x), fmaf(ay, e[i].x, t[i].y), fmaf(ax, e[i].y, t[i].z), fmaf(ay, e[i].y, t[i].w));
+        }
+      }
+      const float c0 = pcs[1][0], s0 = psn[1][0], c1 = pcs[1][1], s1 = psn[1][1];
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+        *(float4*)(X + CH_HIST * 16 + 2 * lane + 64 * i) = make_float4(fmaf(t[i].x, c0, t[i].y * s0), fmaf(t[i].y, c0, -t[i].x * s0),
+                                                                        fmaf(t[i].z, c1, t[i].w * s1), fmaf(t[i].w, c1, -t[i].z * s1));
+    } else {
+#pragma unroll 1
+      for (int i = 0; i < 8; i++) stage_pair(CH_HIST * 16 + 2 * lane + 64 * i, boff, 1);
+    }
     __syncwarp();
     // ---- phase A: branch filters.  Frame kk of the batch sits in X frames kk .. kk + 25 (newest last) --------------------------
 #pragma unroll 1
@@ -253,15 +354,18 @@ __global__ void __launch_bounds__(128, 4) channelize16_kernel(ChanParams p, Chan
       }
     }
     __syncwarp();
+    fast_next = batch < b_last && steady(batch + 1, ca_next);
+    if (fast_next) issue_loads(batch + 1);
     // ---- phase B + C: lane = frame kk = 32 batch + lane ------------------------------------------------------------------------
     {
       float2 v[16];
 #pragma unroll
       for (int n = 0; n < 16; n++) v[n] = V[lane * CH_V_STRIDE + n];
-      dft16<false>(v);
+      dft16p(v);
       const int kk = 32 * batch + lane;
       const bool own = kk >= own_lo && kk < own_hi;
-      const unsigned col = (fs32 + (unsigned)kk) & dmask;
+      float* dptr = drow0 + ((fs32 + (unsigned)kk) & dmask);          // channel c lives demod_stride further per channel
+      float2* cptr = crow0 ? crow0 + (crel + kk) : nullptr;
 #pragma unroll
       for (int c = 0; c < 16; c += 2) {
         const float2 y0 = v[af_dig(c)], y1 = v[af_dig(c + 1)];
@@ -277,13 +381,15 @@ __global__ void __launch_bounds__(128, 4) channelize16_kernel(ChanParams p, Chan
         const float im1 = __fsub_rn(__fmul_rn(p1.x, y1.y), __fmul_rn(p1.y, y1.x));
         const float2 a = fast_atan2f_x2(im0, re0, im1, re1);
         if (own) {
-          drow0[(long long)c * p.demod_stride + col] = a.x * p.ref;
-          drow0[(long long)(c + 1) * p.demod_stride + col] = a.y * p.ref;
-          if (crow0) {
-            crow0[(long long)c * p.chan_ld + crel + kk] = y0;
-            crow0[(long long)(c + 1) * p.chan_ld + crel + kk] = y1;
+          dptr[0] = a.x * p.ref;
+          dptr[p.demod_stride] = a.y * p.ref;
+          if (cptr) {
+            cptr[0] = y0;
+            cptr[p.chan_ld] = y1;
           }
         }
+        dptr += 2 * p.demod_stride;
+        if (cptr) cptr += 2 * p.chan_ld;
         if constexpr (TAPS) {
           if (own) {
             ta.macc[c] += sqrtf(fmaf(y0.x, y0.x, y0.y * y0.y));

@@ -42,33 +42,25 @@ struct Level {
 template <int SRC, int DC, int G, int A, int B, int C, int D, bool ARB>
 static cascade_fn cfn() { return cascade_kernel<SRC, DC, G, A, B, C, D, ARB>; }
 
-// Instantiated stage combinations; anything else is reported as unsupported.
+// Instantiated stage combinations.  msresamp's half-band design (A.3) always yields semi-lengths 3, ..., 3, 5, 10 in
+// execution order, so the groups below ([3,3,3,3], [3,3], [3,5], [3], [5,10], [5], [10] without resampler; [10] / none with it)
+// tile ANY decimating plan: Frontend::init() cuts the stage list greedily into them.
 inline cascade_fn pick_cascade(int src, int dc, bool arb, const int* ms, int* G) {
   auto is = [&](int a, int b, int c, int d) { return ms[0] == a && ms[1] == b && ms[2] == c && ms[3] == d; };
   *G = 16;
+#define PMR_GROUPS(SRC, DC)                                                         \
+  if (is(5, 0, 0, 0)) return cfn<SRC, DC, 16, 5, 0, 0, 0, false>();                 \
+  if (is(5, 10, 0, 0)) return cfn<SRC, DC, 16, 5, 10, 0, 0, false>();               \
+  if (is(3, 5, 0, 0)) return cfn<SRC, DC, 16, 3, 5, 0, 0, false>();                 \
+  if (is(3, 0, 0, 0)) return cfn<SRC, DC, 16, 3, 0, 0, 0, false>();                 \
+  if (is(3, 3, 0, 0)) return cfn<SRC, DC, 16, 3, 3, 0, 0, false>();                 \
+  if (is(3, 3, 3, 3)) return cfn<SRC, DC, 16, 3, 3, 3, 3, false>();   \
+  if (is(10, 0, 0, 0)) return cfn<SRC, DC, 16, 10, 0, 0, 0, false>();
   if (!arb) {
-    if (dc == DC_ZSR && src == SRC_CU8) {
-      if (is(5, 0, 0, 0)) return cfn<SRC_CU8, DC_ZSR, 16, 5, 0, 0, 0, false>();
-      if (is(5, 10, 0, 0)) return cfn<SRC_CU8, DC_ZSR, 16, 5, 10, 0, 0, false>();
-      if (is(3, 5, 0, 0)) return cfn<SRC_CU8, DC_ZSR, 16, 3, 5, 0, 0, false>();
-      if (is(3, 3, 3, 3)) return cfn<SRC_CU8, DC_ZSR, 16, 3, 3, 3, 3, false>();
-    }
-    if (dc == DC_ZSR && src == SRC_CF32) {
-      if (is(5, 0, 0, 0)) return cfn<SRC_CF32, DC_ZSR, 16, 5, 0, 0, 0, false>();
-      if (is(5, 10, 0, 0)) return cfn<SRC_CF32, DC_ZSR, 16, 5, 10, 0, 0, false>();
-      if (is(3, 5, 0, 0)) return cfn<SRC_CF32, DC_ZSR, 16, 3, 5, 0, 0, false>();
-      if (is(3, 3, 3, 3)) return cfn<SRC_CF32, DC_ZSR, 16, 3, 3, 3, 3, false>();
-    }
-    if (dc == DC_NONE && src == SRC_CF32) {   // stand-alone msresamp_crcf (liquid shim): input is already DC-blocked
-      if (is(5, 0, 0, 0)) return cfn<SRC_CF32, DC_NONE, 16, 5, 0, 0, 0, false>();
-      if (is(5, 10, 0, 0)) return cfn<SRC_CF32, DC_NONE, 16, 5, 10, 0, 0, false>();
-      if (is(3, 5, 0, 0)) return cfn<SRC_CF32, DC_NONE, 16, 3, 5, 0, 0, false>();
-      if (is(3, 3, 3, 3)) return cfn<SRC_CF32, DC_NONE, 16, 3, 3, 3, 3, false>();
-    }
-    if (dc == DC_NONE && src == SRC_RING) {
-      if (is(5, 0, 0, 0)) return cfn<SRC_RING, DC_NONE, 16, 5, 0, 0, 0, false>();
-      if (is(3, 5, 0, 0)) return cfn<SRC_RING, DC_NONE, 16, 3, 5, 0, 0, false>();
-    }
+    if (dc == DC_ZSR && src == SRC_CU8) { PMR_GROUPS(SRC_CU8, DC_ZSR) }
+    if (dc == DC_ZSR && src == SRC_CF32) { PMR_GROUPS(SRC_CF32, DC_ZSR) }
+    if (dc == DC_NONE && src == SRC_CF32) { PMR_GROUPS(SRC_CF32, DC_NONE) }   // stand-alone msresamp_crcf (liquid shim): no DC blocker
+    if (dc == DC_NONE && src == SRC_RING) { PMR_GROUPS(SRC_RING, DC_NONE) }
   } else {
     if (dc == DC_NONE && src == SRC_RING && is(10, 0, 0, 0)) { *G = 8; return cfn<SRC_RING, DC_NONE, 8, 10, 0, 0, 0, true>(); }
     if (dc == DC_NONE && src == SRC_RING && is(0, 0, 0, 0)) { *G = 8; return cfn<SRC_RING, DC_NONE, 8, 0, 0, 0, 0, true>(); }
@@ -76,10 +68,58 @@ inline cascade_fn pick_cascade(int src, int dc, bool arb, const int* ms, int* G)
     if (dc == DC_SCAN && src == SRC_CF32 && is(0, 0, 0, 0)) return cfn<SRC_CF32, DC_SCAN, 16, 0, 0, 0, 0, true>();
     if (dc == DC_NONE && src == SRC_CF32 && is(0, 0, 0, 0)) return cfn<SRC_CF32, DC_NONE, 16, 0, 0, 0, 0, true>();
   }
+#undef PMR_GROUPS
   return nullptr;
 }
 
+// Cuts an execution-order stage list (3, ..., 3, 5 [, 10]) into instantiated groups, longest first.
+inline bool cut_groups(std::vector<int> order, std::vector<std::vector<int>>* groups) {
+  static const std::vector<std::vector<int>> known = {{3, 3, 3, 3}, {5, 10}, {3, 5}, {3, 3}, {3}, {5}, {10}};
+  size_t i = 0;
+  while (i < order.size()) {
+    bool hit = false;
+    for (const auto& k : known) {
+      if (i + k.size() > order.size() || !std::equal(k.begin(), k.end(), order.begin() + i)) continue;
+      // [3, 5] would strand a following 3-run; it only matches at the end of the 3s by construction (5 follows the 3s)
+      groups->push_back(k);
+      i += k.size();
+      hit = true;
+      break;
+    }
+    if (!hit) return false;
+  }
+  return true;
+}
+
 struct Frontend {
+  // How a plan is cut into launches (pure host logic, also exported through pmr446_describe_frontend for the CPU tests):
+  // groups[0 .. n-2] are half-band groups, groups[n-1] is the resampler's launch (with the last half-band, or empty).
+  static int plan_groups(const design::MsresampPlan& plan, int in_fmt, std::vector<std::vector<int>>* groups, bool* fused) {
+    // execution-order stage list: plan.m[stages-1] runs first
+    std::vector<int> order;
+    for (int g = (int)plan.stages - 1; g >= 0; g--) order.push_back((int)plan.m[g]);
+    std::vector<int> last;
+    // Two-stage plans whose resampler phase is not periodic (1.024 Msps -> 200 kHz: [5, 10], step 21 474 836): both
+    // half-bands run in the first launch and the last one is the resampler alone -- the ring between them then sits at
+    // the lowest rate (half the traffic) and the per-lane filter-bank gathers no longer share a kernel with the 58-register
+    // m = 10 window.  A single half-band also runs on its own (the resampler kernel with a half-band only reads a ring).
+    // Otherwise the last half-band goes with the resampler (tiled kernel when the phase has period 2).
+    const bool split_arb = (order.size() == 2 && order[0] == 5 && order[1] == 10 && plan.step != (3u << 23)) || order.size() == 1;
+    // 2.4 Msps cu8 -> 200 kHz ([3, 5, 10] + rate 2/3): everything in ONE launch, no intermediate ring (frontend_fused.cuh).
+    // PMR446_FRONTEND=split keeps round 1's two launches (cascade -> 600 kHz ring -> tiled half-band + resampler) for A/B runs.
+    const char* fe_env = getenv("PMR446_FRONTEND");
+    *fused = in_fmt == PMR446_FMT_CU8 && order.size() == 3 && order[0] == 3 && order[1] == 5 && order[2] == 10 &&
+             plan.step == (3u << 23) && !(fe_env && strcmp(fe_env, "split") == 0);
+    if (*fused) {
+      groups->push_back(order);
+    } else {
+      if (!order.empty() && !split_arb) { last.push_back(order.back()); order.pop_back(); }
+      if (!cut_groups(order, groups)) return fail(PMR446_EINVAL, "resampler plan not built: unexpected half-band stage list");
+      groups->push_back(last);   // may be empty (rate >= 0.5)
+    }
+    return 0;
+  }
+
   int S = 0, fmt = 0;
   bool dc = true;
   float alpha = 0.0f, alpha_eff = 0.0f, c_pole = 1.0f;
@@ -166,28 +206,9 @@ struct Frontend {
     if (plan.sub_len != 14) return fail(PMR446_EINVAL, "arbitrary resampler kernel is specialised for 14 taps");
     if (plan.step < (1u << 24)) return fail(PMR446_EINVAL, "internal: decimating plan with arbitrary rate > 1");
     if (plan.bits > 8) return fail(PMR446_EINVAL, "resampler filter bank larger than 256 rows");
-    // execution-order stage list: plan.m[stages-1] runs first
-    std::vector<int> order;
-    for (int g = (int)plan.stages - 1; g >= 0; g--) order.push_back((int)plan.m[g]);
     std::vector<std::vector<int>> groups;   // pre-launch groups, then the arb launch
-    std::vector<int> last;
-    // Two-stage plans whose resampler phase is not periodic (1.024 Msps -> 200 kHz: [5, 10], step 21 474 836): both
-    // half-bands run in the first launch and the last one is the resampler alone -- the ring between them then sits at
-    // the lowest rate (half the traffic) and the per-lane filter-bank gathers no longer share a kernel with the 58-register
-    // m = 10 window.  Otherwise the last half-band goes with the resampler (tiled kernel when the phase has period 2).
-    const bool split_arb = order.size() == 2 && order[0] == 5 && order[1] == 10 && plan.step != (3u << 23);
-    // 2.4 Msps cu8 -> 200 kHz ([3, 5, 10] + rate 2/3): everything in ONE launch, no intermediate ring (frontend_fused.cuh).
-    // PMR446_FRONTEND=split keeps round 1's two launches (cascade -> 600 kHz ring -> tiled half-band + resampler) for A/B runs.
-    const char* fe_env = getenv("PMR446_FRONTEND");
-    const bool want_fused = in_fmt == PMR446_FMT_CU8 && order.size() == 3 && order[0] == 3 && order[1] == 5 && order[2] == 10 &&
-                            plan.step == (3u << 23) && !(fe_env && strcmp(fe_env, "split") == 0);
-    if (want_fused) {
-      groups.push_back(order);
-    } else {
-      if (!order.empty() && !split_arb) { last.push_back(order.back()); order.pop_back(); }
-      for (size_t i = 0; i < order.size(); i += 4) groups.emplace_back(order.begin() + i, order.begin() + std::min(order.size(), i + 4));
-      groups.push_back(last);   // may be empty (rate >= 0.5)
-    }
+    bool want_fused = false;
+    if (int rc = plan_groups(plan, in_fmt, &groups, &want_fused)) return rc;
     levels.resize(groups.size());
     long long max_in = max_chunk;
     int stage_cursor = (int)plan.stages - 1;  // index into plan.m / plan.hb of the next stage to place

@@ -743,6 +743,33 @@ extern "C" int pmr446_design_msresamp(float rate, float as, unsigned* stages, un
   return PMR446_OK;
 }
 
+// How the front end would run msresamp_crcf_create(rate, as) for the given input format: "fused[3,5,10]+arb",
+// "cascade[3,3,3,3] | cascade[3,5] | tile[10]+arb", ... or an error.  Host logic only (no GPU needed).
+extern "C" int pmr446_describe_frontend(float rate, float as, int in_fmt, int with_dc, char* buf, int len) {
+  if (!(rate > 0.0f) || !buf || len < 8) return fail(PMR446_EINVAL, "bad argument");
+  if (rate > 1.0f) return fail(PMR446_EINVAL, "front end only decimates (rate <= 1)");
+  design::MsresampPlan p = design::msresamp_plan(rate, as);
+  std::vector<std::vector<int>> groups;
+  bool fused = false;
+  if (int rc = Frontend::plan_groups(p, in_fmt, &groups, &fused)) return rc;
+  std::string out;
+  for (size_t l = 0; l < groups.size(); l++) {
+    const bool arb = l + 1 == groups.size();
+    const int src = l == 0 ? (in_fmt == PMR446_FMT_CU8 ? SRC_CU8 : SRC_CF32) : SRC_RING;
+    const int dc = (l == 0 && with_dc) ? ((groups.size() >= 2 || fused) ? DC_ZSR : DC_SCAN) : DC_NONE;
+    int ms[4] = {0, 0, 0, 0}, G = 0;
+    for (size_t k = 0; k < groups[l].size() && k < 4; k++) ms[k] = groups[l][k];
+    const bool tile = arb && src == SRC_RING && groups[l].size() == 1 && ms[0] == 10 && p.step == (3u << 23);
+    if (!fused && !tile && !pick_cascade(src, dc, arb, ms, &G)) return fail(PMR446_EINVAL, "resampler plan not built: kernel not instantiated");
+    if (l) out += " | ";
+    out += fused ? "fused[" : (tile ? "tile[" : "cascade[");
+    for (size_t k = 0; k < groups[l].size(); k++) out += (k ? "," : "") + std::to_string(groups[l][k]);
+    out += arb ? "]+arb" : "]";
+  }
+  snprintf(buf, (size_t)len, "%s", out.c_str());
+  return PMR446_OK;
+}
+
 extern "C" int pmr446_design_pfbch(unsigned M, unsigned m, float as, float* taps /*[M][2m]*/) {
   if (!M || !m || !taps) return fail(PMR446_EINVAL, "bad argument");
   std::vector<float> t = design::pfbch_taps(M, m, as);

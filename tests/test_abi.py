@@ -143,3 +143,34 @@ def test_receiver_argument_checks_need_no_device():
     assert L.pmr446_receiver_create(C.byref(cfg), C.byref(h)) == _lib.EINVAL
     assert L.pmr446_receiver_create(None, C.byref(h)) == _lib.EINVAL
     assert L.pmr446_receiver_max_ns(None) == 0 and L.pmr446_receiver_destroy(None) == _lib.OK
+
+
+def test_every_decimating_rate_has_a_frontend_plan():
+    """msresamp_crcf_create(rate, 60) accepts any rate (src/sdr_pmr446.c:425-426): every decimating rate must be cut into
+    instantiated kernels, and the BASELINE plans must keep their intended shape."""
+    import ctypes as C
+
+    import numpy as np
+    from sdr_pmr446_b200 import _lib
+    L = _lib.lib()
+    buf = C.create_string_buffer(256)
+
+    def plan(fs_in, fs_out, fmt):
+        rc = L.pmr446_describe_frontend(np.float32(fs_out) / np.float32(fs_in), 60.0, fmt, 1, buf, 256)
+        assert rc == 0, (fs_in, fs_out, fmt, L.pmr446_last_error())
+        return buf.value.decode()
+
+    assert plan(2400000, 200000, 1) == "fused[3,5,10]+arb"                       # configs[2]: one launch
+    assert plan(2400000, 200000, 0) == "cascade[3,5] | tile[10]+arb"
+    assert plan(1024000, 200000, 1) == "cascade[5,10] | cascade[]+arb"           # configs[0]
+    assert plan(2400000, 12500, 1) == "cascade[3,3,3,3] | cascade[3,5] | tile[10]+arb"   # configs[1]
+    assert plan(20000000, 20000000, 0) == "cascade[]+arb"                        # configs[3]: rate 1.0
+    assert plan(3200000, 200000, 1) == "cascade[3,5] | cascade[10]+arb"
+    rng = np.random.default_rng(7)
+    rates = list(rng.uniform(np.log(1e-4), 0.0, 300))
+    for lr in rates:
+        r = float(np.exp(lr))
+        for fmt in (0, 1):
+            rc = L.pmr446_describe_frontend(np.float32(r), 60.0, fmt, 1, buf, 256)
+            assert rc == 0, (r, fmt, L.pmr446_last_error())
+    assert L.pmr446_describe_frontend(np.float32(1.5), 60.0, 0, 1, buf, 256) != 0      # interpolation is msresamp_rrrf's job (dsd_in)

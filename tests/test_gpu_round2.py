@@ -193,3 +193,32 @@ def test_failed_execute_leaves_state_untouched():
     da.close()
     db.close()
     assert ra["nz"] == rb["nz"] and np.array_equal(ra["pcm"], rb["pcm"])
+
+
+@pytest.mark.parametrize("fs,M,fmt_cu8", [(3200000, 16, True), (1024000, 20, True), (500000, 16, False), (4800000, 16, True)])
+def test_other_resampler_plans(fs, M, fmt_cu8):
+    """msresamp_crcf_create accepts any rate (src/sdr_pmr446.c:425-426).  3.2 Msps -> 200 kHz ([3,5] | [10] + resampler
+    at rate 1/2), 250 kHz output (20 channels from 1.024 Msps), a single half-band (500 kHz -> 200 kHz) and a four-stage
+    plan (4.8 Msps): resampler, channelizer and s16 audio against the oracle."""
+    from oracle import oracle as orc
+    from sdr_pmr446_b200 import chain, synth
+    n = int(fs * 0.15)
+    chunk = n // 3 + 17
+    car = (synth.Carrier(2, 0.2, 1000.0, 67.0), synth.Carrier(M - 1, 0.1, 600.0, 88.5))
+    spec = synth.CaptureSpec(fs=float(fs), num_channels=M, carriers=car)
+    iq = synth.make_cu8(spec, n, 446) if fmt_cu8 else synth.make_cf32(spec, n, 446)
+    fmt = 1 if fmt_cu8 else 0
+    gpu = chain.PmrBatch(n_streams=1, fs_in=fs, in_fmt=fmt, num_channels=M, audio_gain=1.0, max_chunk=chunk)
+    g = gpu.run(iq[None, :], chunk, want=("res", "chan", "demod", "pcm"))
+    gpu.close()
+    o = orc.PmrOracle(fs_in=fs, in_fmt=fmt, num_channels=M, audio_gain=1.0, chunk=chunk)
+    r = o.run(iq, chunk, want=("res", "chan", "demod", "pcm"))
+    o.close()
+    assert g["ny"] == r["ny"] and g["ns"] == r["ns"]
+    assert rel_rms(g["res"][0], r["res"]) < REL_RMS_TOL
+    assert rel_rms(g["chan"][0], r["chan"]) < REL_RMS_TOL
+    for c in active_channels(car):
+        sl = slice(1, None) if g["demod"][0, c, 0] == r["demod"][c, 0] else slice(500, None)
+        assert rel_rms(g["demod"][0, c, sl], r["demod"][c, sl]) < REL_RMS_TOL, ("demod", c)
+        dp = np.abs(g["pcm"][0, c, 600:].astype(np.int32) - r["pcm"][c, 600:].astype(np.int32))
+        assert dp.max() <= PCM_TOL_LSB, ("pcm", c, int(dp.max()))

@@ -13,7 +13,7 @@ __device__ __forceinline__ float ffma1(float a, float b, float c) {
   asm volatile("fma.rn.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
 }
-template <int NCH, bool PACKED>
+template <int NCH, bool PACKED, bool VIA_C = false>
 __global__ void __launch_bounds__(128) lat(float* out, long long* cyc, int iters, float a, float b) {
   float2 x[NCH];
 #pragma unroll
@@ -25,7 +25,8 @@ __global__ void __launch_bounds__(128) lat(float* out, long long* cyc, int iters
     for (int u = 0; u < 64 / NCH; u++) {
 #pragma unroll
       for (int i = 0; i < NCH; i++) {
-        if (PACKED) x[i] = ffma2(x[i], aa, bb);
+        if (PACKED && VIA_C) x[i] = ffma2(aa, bb, x[i]);   // dependency through the addend, as in a FIR accumulation
+        else if (PACKED) x[i] = ffma2(x[i], aa, bb);
         else x[i].x = ffma1(x[i].x, a, b);
       }
     }
@@ -37,18 +38,19 @@ __global__ void __launch_bounds__(128) lat(float* out, long long* cyc, int iters
   if (s == 1234.5f) out[0] = s;
   if (threadIdx.x == 0 && blockIdx.x == 0) cyc[0] = t1 - t0;
 }
-template <int NCH, bool PACKED>
+template <int NCH, bool PACKED, bool VIA_C = false>
 void run() {
   float* d; long long* c; cudaMalloc(&d, 4); cudaMalloc(&c, 8);
   const int iters = 4096;
-  lat<NCH, PACKED><<<148, 128>>>(d, c, iters, 0.999f, 0.001f);
-  lat<NCH, PACKED><<<148, 128>>>(d, c, iters, 0.999f, 0.001f);
+  lat<NCH, PACKED, VIA_C><<<148, 128>>>(d, c, iters, 0.999f, 1e-9f);
+  lat<NCH, PACKED, VIA_C><<<148, 128>>>(d, c, iters, 0.999f, 1e-9f);
   long long h = 0; cudaMemcpy(&h, c, 8, cudaMemcpyDeviceToHost);
-  printf("{\"op\": \"%s\", \"chains\": %d, \"cycles_per_instr\": %.2f}\n", PACKED ? "FFMA2" : "FFMA", NCH, (double)h / ((double)iters * 64));
+  printf("{\"op\": \"%s%s\", \"chains\": %d, \"cycles_per_instr\": %.2f}\n", PACKED ? "FFMA2" : "FFMA", VIA_C ? " (chain through addend)" : "", NCH, (double)h / ((double)iters * 64));
   cudaFree(d); cudaFree(c);
 }
 int main() {
   run<1, false>(); run<2, false>(); run<4, false>(); run<8, false>();
   run<1, true>(); run<2, true>(); run<4, true>(); run<8, true>(); run<16, true>();
+  run<1, true, true>(); run<2, true, true>(); run<3, true, true>(); run<4, true, true>(); run<8, true, true>();
   return cudaDeviceSynchronize() != cudaSuccess;
 }
