@@ -1,0 +1,180 @@
+// wf_accumulate_fast_kernel: the asgram / spgram periodogram (/root/reference/src/sdr_pmr446.c:473-477, :910-913; SURVEY.md
+// Appendix A.13) for widths W = 8 P with a small smooth P (W = 120: P = 15, the 480-point transform of a 120-column
+// terminal), one WARP per transform and nothing but registers between the stages.
+//
+// The transform is zero-padded: X[k] = sum_{n < W} x[n] w[n] e^{-2 pi i n k / 4W}.  With k = 4 q + r this is, for each of
+// the four residues r, a W-point DFT of the pre-twiddled window x_r[n] = x[n] w[n] W_4W^{n r} -- four independent
+// 8P-point transforms, one per quarter-warp:
+//   lane = (r, l): holds x_r[l + 8 m], m < P (the window value and the pre-twiddle are one complex constant per register)
+//   1. P-point DFT over m in registers (compile-time mixed radix 2/3/4/5, twiddles from the kernel parameters),
+//   2. twiddle W_8P^{l k2} (lane constants),
+//   3. 8-point DFT over the quarter-warp's lanes: transposed through 8 x P float2 of shared memory per quarter-warp, each
+//      lane then runs one or two 8-point DFTs in registers,
+//   4. |X|^2 accumulated in registers across all the transforms the warp walks; written once per block.
+// Round 1's warp kernel kept every stage in shared memory (a mixed-radix Stockham pass per factor): 7.6 ms per 1024-stream
+// step at W = 120; the generic kernels remain for every other width.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "audio_fft.cuh"   // cmul
+#include "spectrum.cuh"    // dft3, dft5, WfParams
+
+namespace pmr {
+
+constexpr int WFF_MAXP = 20;
+
+struct WfFastParams {
+  WfParams w;
+  float2 twp[WFF_MAXP];   // W_P^m, m < P
+};
+
+// in-register DFT of compile-time size P = 2^a 3^b 5^c (decimation in time): y[k] = sum_n x[n stride] W_P^{n k}
+// TW = stride of this level's twiddles in the W_P0 table (W_P^m = table[m * TW])
+template <int P, int TW>
+struct RegDft {
+  static constexpr int R = (P % 4 == 0) ? 4 : (P % 2 == 0) ? 2 : (P % 3 == 0) ? 3 : (P % 5 == 0) ? 5 : P;
+  static constexpr int Q = P / R;
+  static_assert(R == 2 || R == 3 || R == 4 || R == 5, "P must factor into 2, 3 and 5");
+  __device__ __forceinline__ static void run(const float2* x, int stride, float2* y, const float2* tw) {
+    // n = Q n1 + n2, k = k1 + R k2:  X[k1 + R k2] = sum_n2 W_P^{n2 k1} ( sum_n1 x[Q n1 + n2] W_R^{n1 k1} ) W_Q^{n2 k2}
+    float2 a[Q][R];
+#pragma unroll
+    for (int n2 = 0; n2 < Q; n2++) {
+      float2 v[R];
+#pragma unroll
+      for (int n1 = 0; n1 < R; n1++) v[n1] = x[(Q * n1 + n2) * stride];
+      if (R == 2) {
+        const float2 t = v[0];
+        v[0] = make_float2(t.x + v[1].x, t.y + v[1].y);
+        v[1] = make_float2(t.x - v[1].x, t.y - v[1].y);
+      } else if (R == 4) {
+        dft4<false>(v[0], v[1], v[2], v[3]);
+      } else if (R == 3) {
+        dft3(v);
+      } else {
+        dft5(v);
+      }
+#pragma unroll
+      for (int k1 = 0; k1 < R; k1++) a[n2][k1] = (n2 * k1 == 0) ? v[k1] : cmul(v[k1], tw[((n2 * k1) % P) * TW]);
+    }
+    if (Q == 1) {
+#pragma unroll
+      for (int k1 = 0; k1 < R; k1++) y[k1] = a[0][k1];
+    } else {
+#pragma unroll
+      for (int k1 = 0; k1 < R; k1++) {
+        float2 col[Q], out[Q];
+#pragma unroll
+        for (int n2 = 0; n2 < Q; n2++) col[n2] = a[n2][k1];
+        RegDft<Q, TW * R>::run(col, 1, out, tw);
+#pragma unroll
+        for (int k2 = 0; k2 < Q; k2++) y[k1 + R * k2] = out[k2];
+      }
+    }
+  }
+};
+template <int TW>
+struct RegDft<1, TW> {
+  __device__ __forceinline__ static void run(const float2* x, int stride, float2* y, const float2*) { y[0] = x[0]; }
+};
+
+// forward 8-point DFT in registers, natural order in and out
+__device__ __forceinline__ void dft8(float2* v) {
+  const float r = 0.70710678118654752f;
+  float2 e[4] = {v[0], v[2], v[4], v[6]}, o[4] = {v[1], v[3], v[5], v[7]};
+  dft4<false>(e[0], e[1], e[2], e[3]);
+  dft4<false>(o[0], o[1], o[2], o[3]);
+  // W8^k o[k]: W8 = (1 - i) / sqrt 2
+  const float2 o1 = make_float2(r * (o[1].x + o[1].y), r * (o[1].y - o[1].x));
+  const float2 o2 = make_float2(o[2].y, -o[2].x);
+  const float2 o3 = make_float2(r * (o[3].y - o[3].x), -r * (o[3].x + o[3].y));
+  v[0] = make_float2(e[0].x + o[0].x, e[0].y + o[0].y); v[4] = make_float2(e[0].x - o[0].x, e[0].y - o[0].y);
+  v[1] = make_float2(e[1].x + o1.x, e[1].y + o1.y);     v[5] = make_float2(e[1].x - o1.x, e[1].y - o1.y);
+  v[2] = make_float2(e[2].x + o2.x, e[2].y + o2.y);     v[6] = make_float2(e[2].x - o2.x, e[2].y - o2.y);
+  v[3] = make_float2(e[3].x + o3.x, e[3].y + o3.y);     v[7] = make_float2(e[3].x - o3.x, e[3].y - o3.y);
+}
+
+constexpr int WFF_WARPS = 8;
+
+template <int P>
+__global__ void __launch_bounds__(32 * WFF_WARPS) wf_accumulate_fast_kernel(WfFastParams fp) {
+  const WfParams& p = fp.w;
+  constexpr int W = 8 * P;
+  constexpr int NC = (P + 7) / 8;                           // DFT8 columns per lane (k2 = l, l + 8, ...)
+  __shared__ float2 xch[WFF_WARPS][4][8 * P + 1];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int r = lane >> 3, l = lane & 7;
+  float2* const xq = xch[wp][r];
+  const int s = blockIdx.x / p.parts, part = blockIdx.x % p.parts;
+  const float2* res = p.res + (long long)s * p.res_stride;
+  // lane constants: window x pre-twiddle W_4W^{n r} for n = l + 8 m, and the inter-stage twiddle W_8P^{l k2}
+  float2 cw[P], t2[P];
+#pragma unroll
+  for (int m = 0; m < P; m++) {
+    const int n = l + 8 * m;
+    const float2 t = p.twiddle[(n * r) % (4 * W)];          // table of W_4W^k
+    const float wv = p.window[n];
+    cw[m] = make_float2(wv * t.x, wv * t.y);
+    t2[m] = p.twiddle[(4 * l * m) % (4 * W)];               // W_8P^{l m} = W_4W^{4 l m}
+  }
+  float acc[NC][8];
+#pragma unroll
+  for (int c = 0; c < NC; c++)
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[c][k] = 0.0f;
+
+  const int nw = blockDim.x >> 5;
+  const unsigned r0 = (unsigned)p.r0, rmask = (unsigned)p.res_mask;
+  auto load = [&](int t, float2* x) {
+    const int first = t * p.hop - W;                        // chunk-local index of window sample 0 (may be negative: zeros)
+#pragma unroll
+    for (int m = 0; m < P; m++) {
+      const int li = first + l + 8 * m;
+      x[m] = li >= 0 ? res[(r0 + (unsigned)li) & rmask] : make_float2(0.0f, 0.0f);
+    }
+  };
+  int t = 1 + part + p.parts * wp;
+  const int tstep = p.parts * nw;
+  float2 xn[P];
+  if (t <= p.n_transforms) load(t, xn);
+  for (; t <= p.n_transforms; t += tstep) {
+    float2 x[P], y[P];
+#pragma unroll
+    for (int m = 0; m < P; m++) x[m] = cmul(xn[m], cw[m]);
+    if (t + tstep <= p.n_transforms) load(t + tstep, xn);   // next transform's samples in flight during this one
+    RegDft<P, 1>::run(x, 1, y, fp.twp);
+#pragma unroll
+    for (int k2 = 0; k2 < P; k2++) xq[l * P + k2] = (l == 0 || k2 == 0) ? y[k2] : cmul(y[k2], t2[k2]);
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      const int k2 = l + 8 * c;
+      if (k2 < P) {
+        float2 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = xq[j * P + k2];
+        dft8(v);
+#pragma unroll
+        for (int k1 = 0; k1 < 8; k1++) acc[c][k1] = fmaf(v[k1].x, v[k1].x, fmaf(v[k1].y, v[k1].y, acc[c][k1]));
+      }
+    }
+    __syncwarp();
+  }
+  // block reduction: bin k = 4 q + r with q = k2 + P k1
+  __shared__ float red[4 * W];
+  for (int i = threadIdx.x; i < 4 * W; i += blockDim.x) red[i] = 0.0f;
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    const int k2 = l + 8 * c;
+    if (k2 < P) {
+#pragma unroll
+      for (int k1 = 0; k1 < 8; k1++) atomicAdd(&red[4 * (k2 + P * k1) + r], acc[c][k1]);
+    }
+  }
+  __syncthreads();
+  float* out = p.partial + ((long long)s * p.parts + part) * (4 * W);
+  for (int i = threadIdx.x; i < 4 * W; i += blockDim.x) out[i] = red[i];
+}
+
+}  // namespace pmr
