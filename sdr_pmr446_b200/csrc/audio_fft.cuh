@@ -17,6 +17,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "packed_f32.cuh"
+
 namespace pmr {
 
 // PMR audio float -> s16: (int16_t)(v * 32767) like src/dsd_in.c:172-175, but SATURATING.  The reference's PMR path hands
@@ -47,8 +49,8 @@ struct AudioFftParams {
   long long out_ld;
 };
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return fadd2(a, b); }   // one packed FADD2 (same rounding as two FADDs)
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return fsub2(a, b); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x)); }
 
 // 4-point DFT in place: (a, b, c, d) -> (y0, y1, y2, y3); INV conjugates the kernel

@@ -110,9 +110,9 @@ __device__ __forceinline__ float2 fast_atan2f_x2(float y0, float x0, float y1, f
 // additions as packed FADD2: 6 packed + 4 scalar instructions per radix-4 butterfly instead of 16 scalar ones
 __device__ __forceinline__ void dft4p(float2& a, float2& b, float2& c, float2& d) {
   const float2 s0 = fadd2(a, c), s2 = fadd2(b, d);
-  const float2 s1 = fadd2(a, make_float2(-c.x, -c.y)), s3 = fadd2(b, make_float2(-d.x, -d.y));
+  const float2 s1 = fsub2(a, c), s3 = fsub2(b, d);
   a = fadd2(s0, s2);
-  c = fadd2(s0, make_float2(-s2.x, -s2.y));
+  c = fsub2(s0, s2);
   b = make_float2(s1.x + s3.y, s1.y - s3.x);
   d = make_float2(s1.x - s3.y, s1.y + s3.x);
 }

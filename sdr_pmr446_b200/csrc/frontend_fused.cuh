@@ -22,27 +22,9 @@
 #include <type_traits>
 
 #include "frontend.cuh"
+#include "packed_f32.cuh"
 
 namespace pmr {
-
-// ---- packed FP32 (sm_100: FFMA2 / FADD2 / FMUL2) ---------------------------------------------------------------------
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-  float2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(*(unsigned long long*)&d) : "l"(*(unsigned long long*)&a), "l"(*(unsigned long long*)&b), "l"(*(unsigned long long*)&c));
-  return d;
-}
-__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
-  float2 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(*(unsigned long long*)&d) : "l"(*(unsigned long long*)&a), "l"(*(unsigned long long*)&b));
-  return d;
-}
-__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
-  float2 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(*(unsigned long long*)&d) : "l"(*(unsigned long long*)&a), "l"(*(unsigned long long*)&b));
-  return d;
-}
-// scalar tap times a pair: ptxas emits the scalar-broadcast operand form (R.F32 / UR.F32), no duplicate register
-__device__ __forceinline__ float2 fma_tap(float h, float2 x, float2 acc) { return ffma2(make_float2(h, h), x, acc); }
 
 constexpr int FF_THREADS = 128;
 constexpr int FF_SLOTS = 29 + 13;   // shared-memory history per thread: m = 10 stage (19 even + 10 odd) + resampler window (13)

@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "common_host.hpp"
@@ -370,6 +372,10 @@ static __global__ void __launch_bounds__(256) wf_finalize_kernel(WfFinalParams p
   }
 }
 
+}  // namespace pmr
+#include "spectrum_fast.cuh"
+namespace pmr {
+
 // init() and execute() are force-inlined: the kernels above are static (one copy per translation unit), so the code that
 // sets their attributes and launches them must not be merged across translation units by the linker either.
 struct Waterfall {
@@ -382,6 +388,8 @@ struct Waterfall {
   size_t smem = 0;
   bool warp_kernel = false;   // nfft <= 1024: one warp per transform
   int wf_warps = 1;
+  int fast_p = 0;             // W = 8 P with P in {8, 10, 12, 15, 16, 20}: register-resident kernel (spectrum_fast.cuh)
+  float2 twp[WFF_MAXP];
 
   __attribute__((always_inline)) inline int init(int n_streams, unsigned width) {
     S = n_streams;
@@ -403,12 +411,24 @@ struct Waterfall {
     }
     // enough (stream, part) blocks to fill the GPU: one block needs nfft * 20 bytes of shared memory (block-per-transform
     // kernel) or nfft * 8 * (1 + 2 * 8 warps) bytes (warp-per-transform kernel, nfft <= 1024)
+    {
+      const char* env = getenv("PMR446_WATERFALL");   // "generic" keeps round 1's shared-memory kernels (A/B runs)
+      const unsigned P = W / 8;
+      if (W % 8 == 0 && (P == 8 || P == 10 || P == 12 || P == 15 || P == 16 || P == 20) && !(env && strcmp(env, "generic") == 0)) {
+        fast_p = (int)P;
+        for (unsigned m = 0; m < P; m++) {
+          const double a = -2.0 * M_PI * (double)m / (double)P;
+          twp[m] = make_float2((float)cos(a), (float)sin(a));
+        }
+      }
+    }
     warp_kernel = nfft <= 1024;
     wf_warps = std::max(1, std::min(WFW_WARPS, (int)((96 * 1024 / (nfft * sizeof(float2)) - 1) / 2)));
     {
       const size_t per_block = warp_kernel ? (size_t)nfft * sizeof(float2) * (1 + 2 * wf_warps) : (size_t)nfft * (2 * sizeof(float2) + sizeof(float));
-      const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / per_block));
-      parts = std::max(1, std::min(128, (148 * per_sm + S - 1) / S));
+      const int per_sm = fast_p ? 3 : (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / per_block));
+      // the fast kernel's blocks are long (a whole stream's transforms): eight waves of them keep the tail short
+      parts = std::max(1, std::min(128, ((fast_p ? 8 : 1) * 148 * per_sm + S - 1) / S));
     }
     int rc;
     if ((rc = d_window.alloc(W * sizeof(float))) || (rc = d_twiddle.alloc(nfft * sizeof(float2))) ||
@@ -445,7 +465,21 @@ struct Waterfall {
     p.n_stages = (int)radix.size();
     for (size_t i = 0; i < radix.size(); i++) p.radix[i] = radix[i];
     p.partial = (float*)d_partial.p;
-    if (p.n_transforms > 0) {
+    if (p.n_transforms > 0 && fast_p) {
+      WfFastParams fpar;
+      fpar.w = p;
+      memcpy(fpar.twp, twp, sizeof twp);
+      const unsigned grid = (unsigned)(S * parts), thr = 32 * WFF_WARPS;
+      switch (fast_p) {
+        case 8: wf_accumulate_fast_kernel<8><<<grid, thr, 0, st>>>(fpar); break;
+        case 10: wf_accumulate_fast_kernel<10><<<grid, thr, 0, st>>>(fpar); break;
+        case 12: wf_accumulate_fast_kernel<12><<<grid, thr, 0, st>>>(fpar); break;
+        case 15: wf_accumulate_fast_kernel<15><<<grid, thr, 0, st>>>(fpar); break;
+        case 16: wf_accumulate_fast_kernel<16><<<grid, thr, 0, st>>>(fpar); break;
+        default: wf_accumulate_fast_kernel<20><<<grid, thr, 0, st>>>(fpar); break;
+      }
+      (*launches)++;
+    } else if (p.n_transforms > 0) {
       // a large transform leaves room for one block per SM only: give it 32 warps to hide the shared-memory latency
       if (warp_kernel && nfft <= 256) wf_accumulate_warp_kernel<8><<<S * parts, 32 * wf_warps, smem, st>>>(p);
       else if (warp_kernel && nfft <= 512) wf_accumulate_warp_kernel<16><<<S * parts, 32 * wf_warps, smem, st>>>(p);

@@ -17,7 +17,7 @@
 #include <cuda_runtime.h>
 
 #include "audio_fft.cuh"   // cmul
-#include "spectrum.cuh"    // dft3, dft5, WfParams
+// included from spectrum.cuh (dft3, dft5, WfParams are defined above the include point)
 
 namespace pmr {
 
@@ -94,14 +94,15 @@ __device__ __forceinline__ void dft8(float2* v) {
   v[3] = make_float2(e[3].x + o3.x, e[3].y + o3.y);     v[7] = make_float2(e[3].x - o3.x, e[3].y - o3.y);
 }
 
-constexpr int WFF_WARPS = 8;
+constexpr int WFF_WARPS = 4;   // 128 threads, ~165 registers: three blocks = twelve warps per SM
 
 template <int P>
-__global__ void __launch_bounds__(32 * WFF_WARPS) wf_accumulate_fast_kernel(WfFastParams fp) {
+__global__ void __launch_bounds__(32 * WFF_WARPS, 3) wf_accumulate_fast_kernel(WfFastParams fp) {
   const WfParams& p = fp.w;
   constexpr int W = 8 * P;
   constexpr int NC = (P + 7) / 8;                           // DFT8 columns per lane (k2 = l, l + 8, ...)
-  __shared__ float2 xch[WFF_WARPS][4][8 * P + 1];
+  constexpr int PS = P | 1;                                 // odd row stride: the eight lanes of a quarter-warp hit eight banks
+  __shared__ float2 xch[WFF_WARPS][4][8 * PS + 1];
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   const int r = lane >> 3, l = lane & 7;
   float2* const xq = xch[wp][r];
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(32 * WFF_WARPS) wf_accumulate_fast_kernel(WfFa
     if (t + tstep <= p.n_transforms) load(t + tstep, xn);   // next transform's samples in flight during this one
     RegDft<P, 1>::run(x, 1, y, fp.twp);
 #pragma unroll
-    for (int k2 = 0; k2 < P; k2++) xq[l * P + k2] = (l == 0 || k2 == 0) ? y[k2] : cmul(y[k2], t2[k2]);
+    for (int k2 = 0; k2 < P; k2++) xq[l * PS + k2] = (l == 0 || k2 == 0) ? y[k2] : cmul(y[k2], t2[k2]);
     __syncwarp();
 #pragma unroll
     for (int c = 0; c < NC; c++) {
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(32 * WFF_WARPS) wf_accumulate_fast_kernel(WfFa
       if (k2 < P) {
         float2 v[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) v[j] = xq[j * P + k2];
+        for (int j = 0; j < 8; j++) v[j] = xq[j * PS + k2];
         dft8(v);
 #pragma unroll
         for (int k1 = 0; k1 < 8; k1++) acc[c][k1] = fmaf(v[k1].x, v[k1].x, fmaf(v[k1].y, v[k1].y, acc[c][k1]));
@@ -160,21 +161,25 @@ __global__ void __launch_bounds__(32 * WFF_WARPS) wf_accumulate_fast_kernel(WfFa
     }
     __syncwarp();
   }
-  // block reduction: bin k = 4 q + r with q = k2 + P k1
-  __shared__ float red[4 * W];
-  for (int i = threadIdx.x; i < 4 * W; i += blockDim.x) red[i] = 0.0f;
+  // block reduction in a fixed order (bit-reproducible): every warp parks its bins -- bin k = 4 q + r with
+  // q = k2 + P k1 -- in the idle exchange buffer, then the block adds the warps in order
   __syncthreads();
+  float* red = (float*)&xch[0][0][0];                        // [warps][4 W] floats: half of the exchange buffer
 #pragma unroll
   for (int c = 0; c < NC; c++) {
     const int k2 = l + 8 * c;
     if (k2 < P) {
 #pragma unroll
-      for (int k1 = 0; k1 < 8; k1++) atomicAdd(&red[4 * (k2 + P * k1) + r], acc[c][k1]);
+      for (int k1 = 0; k1 < 8; k1++) red[wp * (4 * W) + 4 * (k2 + P * k1) + r] = acc[c][k1];
     }
   }
   __syncthreads();
   float* out = p.partial + ((long long)s * p.parts + part) * (4 * W);
-  for (int i = threadIdx.x; i < 4 * W; i += blockDim.x) out[i] = red[i];
+  for (int i = threadIdx.x; i < 4 * W; i += blockDim.x) {
+    float sum = 0.0f;
+    for (int q = 0; q < nw; q++) sum += red[q * (4 * W) + i];
+    out[i] = sum;
+  }
 }
 
 }  // namespace pmr
