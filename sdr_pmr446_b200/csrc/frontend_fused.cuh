@@ -85,6 +85,17 @@ __device__ __forceinline__ float2 cu8_pair(unsigned w, int k) {
   return ffma2(u, make_float2(1.0f / 128.0f, 1.0f / 128.0f), make_float2(-127.4f / 128.0f, -127.4f / 128.0f));
 }
 
+// The same conversion as a table look-up: 256 entries, each replicated for the 32 lanes at a 256-byte pitch, so ONE PRMT
+// builds the shared-memory byte offset (byte 1 = the sample byte, byte 0 = 4 * lane) and the load is conflict-free (bank =
+// lane).  Takes the FADD2 + FFMA2 per sample (15 % of the kernel's FMA-pipe work) off the FMA pipe and puts two LDS.32 on
+// the otherwise idle load/store pipe.  64 KB of shared memory per block.
+constexpr int FF_LUT_BYTES = 256 * 256;
+__device__ __forceinline__ float2 cu8_pair_lut(const char* lut, unsigned lane4, unsigned w, int k) {
+  const unsigned o0 = __byte_perm(w, lane4, 0x5504u + ((unsigned)(2 * k) << 4));
+  const unsigned o1 = __byte_perm(w, lane4, 0x5504u + ((unsigned)(2 * k + 1) << 4));
+  return make_float2(*(const float*)(lut + o0), *(const float*)(lut + o1));
+}
+
 constexpr int FF_G = 48;        // input samples per iteration
 constexpr int FF_SUB = 16;      // ... in three sub-blocks of 16 (32 bytes of cu8)
 constexpr int FF_D = 8;         // decimation of the three half-bands
@@ -100,8 +111,17 @@ __device__ __forceinline__ void ldg256_nc(const void* p, unsigned* w) {
 // stages that run once per iteration (m = 10 half-band, resampler) live in shared memory (42 slots x 128 threads x 8 B =
 // 43 KB, thread-private columns: a warp's access to one slot is 256 contiguous bytes), 167 registers, 3 blocks per SM --
 // measured 2.75 ms against 2.68 ms (1024 streams), so occupancy is not what limits this kernel.
-template <int DC, int NB = 2, bool SMH = false>
+template <int DC, int NB = 2, bool SMH = false, bool LUT = false>
 __global__ void __launch_bounds__(FF_THREADS, NB) fused_frontend_kernel(FusedParams fp) {
+  extern __shared__ __align__(16) char ff_lut[];   // LUT only: FF_LUT_BYTES of dynamic shared memory
+  const unsigned lane4 = (threadIdx.x & 31u) * 4u;
+  if (LUT) {
+    for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) {
+      const int b = i >> 5, ln = i & 31;
+      *(float*)(ff_lut + b * 256 + ln * 4) = fmaf((float)b, 1.0f / 128.0f, -127.4f / 128.0f);   // exact, as cu8_pair
+    }
+    __syncthreads();
+  }
   __shared__ float2 ff_hist[SMH ? FF_SLOTS * FF_THREADS : 1];
   float2* const smc = ff_hist + (SMH ? threadIdx.x : 0);
   float2* const sma = smc + (SMH ? 29 * FF_THREADS : 0);
@@ -182,7 +202,10 @@ __global__ void __launch_bounds__(FF_THREADS, NB) fused_frontend_kernel(FusedPar
       float2 x[FF_SUB];
       if (FAST) {
 #pragma unroll
-        for (int j = 0; j < FF_SUB / 2; j++) { x[2 * j] = cu8_pair(raw[sub].w[j], 0); x[2 * j + 1] = cu8_pair(raw[sub].w[j], 1); }
+        for (int j = 0; j < FF_SUB / 2; j++) {
+          x[2 * j] = LUT ? cu8_pair_lut(ff_lut, lane4, raw[sub].w[j], 0) : cu8_pair(raw[sub].w[j], 0);
+          x[2 * j + 1] = LUT ? cu8_pair_lut(ff_lut, lane4, raw[sub].w[j], 1) : cu8_pair(raw[sub].w[j], 1);
+        }
       } else {
         float xr[FF_SUB], xi[FF_SUB];
         ld.template convert<FF_SUB>(p.src, qb + (long long)sbi * FF_SUB, sbi, raw[sub], xr, xi);

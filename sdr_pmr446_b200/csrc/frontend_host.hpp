@@ -257,6 +257,7 @@ struct Frontend {
         L.halo = (halo + L.D + FF_G - 1) / FF_G * FF_G;
         int sl = 6144;
         while (sl > 1536 && (long long)S * ((max_in + sl - 1) / sl) < 148LL * 256) sl >>= 1;
+        if (getenv("PMR446_FF_SEG")) sl = atoi(getenv("PMR446_FF_SEG"));   // tuning probe: 1536 / 3072 / 6144 / 12288
         L.seg_len = sl;
         for (int r = 0; r < 2; r++) {
           const unsigned row = (unsigned)((((unsigned long long)r * plan.step) & ((1u << 24) - 1)) >> (24 - plan.bits));
@@ -479,9 +480,18 @@ struct Frontend {
           memcpy(cp.hb, L.hb, sizeof cp.hb);
           memcpy(fp.arb, L.arb_rows, sizeof fp.arb);
           static const bool smem3 = getenv("PMR446_FF_VARIANT") && strcmp(getenv("PMR446_FF_VARIANT"), "smem3") == 0;   // tuning probe
-          if (L.dc != DC_ZSR) fused_frontend_kernel<DC_NONE><<<blocks, FF_THREADS, 0, st>>>(fp);
+          static const bool lut_cvt = [] {
+            const bool on = getenv("PMR446_FF_CVT") && strcmp(getenv("PMR446_FF_CVT"), "lut") == 0;
+            if (on) cudaFuncSetAttribute(fused_frontend_kernel<DC_ZSR, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_LUT_BYTES);
+            return on;
+          }();
+          static const int thr_env = getenv("PMR446_FF_THREADS") ? atoi(getenv("PMR446_FF_THREADS")) : 0;   // tuning probe: 32 / 64
+          const int thr = (thr_env == 32 || thr_env == 64) && !smem3 ? thr_env : FF_THREADS;
+          const unsigned fblocks = (unsigned)((threads + thr - 1) / thr);
+          if (L.dc != DC_ZSR) fused_frontend_kernel<DC_NONE><<<fblocks, thr, 0, st>>>(fp);
           else if (smem3) fused_frontend_kernel<DC_ZSR, 3, true><<<blocks, FF_THREADS, 0, st>>>(fp);
-          else fused_frontend_kernel<DC_ZSR><<<blocks, FF_THREADS, 0, st>>>(fp);
+          else if (lut_cvt) fused_frontend_kernel<DC_ZSR, 2, false, true><<<fblocks, thr, FF_LUT_BYTES, st>>>(fp);
+          else fused_frontend_kernel<DC_ZSR><<<fblocks, thr, 0, st>>>(fp);
           *launches += 1;
           tm->mark(st, TM_CASCADE0);
           if (out1 > out0) new_out = (long long)design::arb_outputs_after((uint64_t)out1, plan.step);
