@@ -25,6 +25,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "packed_f32.cuh"
+
 namespace pmr {
 
 enum { SRC_CU8 = 0, SRC_CF32 = 1, SRC_RING = 2 };
@@ -295,43 +297,38 @@ struct Loader<SRC_RING> {
 
 // ---- one half-band decimator stage held in registers (A.4) ------------------------------
 //   out[o] = x_odd[o - M] + sum_{j<2M} h[j] * x_even[o - j]
-// processes B input pairs per call; STAGE selects the row of CascadeParams::hb.
+// processes B input pairs per call; STAGE selects the row of CascadeParams::hb.  Samples are (re, im) register pairs and
+// every tap is one packed FFMA2 with the tap as a scalar constant-bank / uniform-register operand (packed_f32.cuh).
 template <int M, int B, int STAGE>
 struct HbStage {
-  float her[2 * M - 1], hei[2 * M - 1];  // previous even samples, oldest first
-  float hor_[M], hoi[M];                 // previous odd samples, oldest first
+  float2 he[2 * M - 1];  // previous even samples, oldest first
+  float2 ho[M];          // previous odd samples, oldest first
   __device__ __forceinline__ void reset() {
 #pragma unroll
-    for (int i = 0; i < 2 * M - 1; i++) her[i] = hei[i] = 0.0f;
+    for (int i = 0; i < 2 * M - 1; i++) he[i] = make_float2(0.0f, 0.0f);
 #pragma unroll
-    for (int i = 0; i < M; i++) hor_[i] = hoi[i] = 0.0f;
+    for (int i = 0; i < M; i++) ho[i] = make_float2(0.0f, 0.0f);
   }
-  __device__ __forceinline__ void run(const CascadeParams& p, const float* xr, const float* xi, float* yr, float* yi, float scale) {
-    float er[2 * M - 1 + B], ei[2 * M - 1 + B], or_[M + B], oi[M + B];
+  template <bool SCALE>
+  __device__ __forceinline__ void run(const CascadeParams& p, const float2* x, float2* y, float scale) {
+    float2 e[2 * M - 1 + B], o[M + B];
 #pragma unroll
-    for (int i = 0; i < 2 * M - 1; i++) { er[i] = her[i]; ei[i] = hei[i]; }
+    for (int i = 0; i < 2 * M - 1; i++) e[i] = he[i];
 #pragma unroll
-    for (int i = 0; i < M; i++) { or_[i] = hor_[i]; oi[i] = hoi[i]; }
+    for (int i = 0; i < M; i++) o[i] = ho[i];
 #pragma unroll
-    for (int b = 0; b < B; b++) {
-      er[2 * M - 1 + b] = xr[2 * b]; ei[2 * M - 1 + b] = xi[2 * b];
-      or_[M + b] = xr[2 * b + 1];    oi[M + b] = xi[2 * b + 1];
-    }
+    for (int b = 0; b < B; b++) { e[2 * M - 1 + b] = x[2 * b]; o[M + b] = x[2 * b + 1]; }
 #pragma unroll
     for (int b = 0; b < B; b++) {
-      float ar = or_[b], ai = oi[b];
+      float2 acc = o[b];
 #pragma unroll
-      for (int j = 0; j < 2 * M; j++) {
-        ar = fmaf(p.hb[STAGE][j], er[2 * M - 1 + b - j], ar);
-        ai = fmaf(p.hb[STAGE][j], ei[2 * M - 1 + b - j], ai);
-      }
-      yr[b] = ar * scale;
-      yi[b] = ai * scale;
+      for (int j = 0; j < 2 * M; j++) acc = fma_tap(p.hb[STAGE][j], e[2 * M - 1 + b - j], acc);
+      y[b] = SCALE ? fmul2(acc, make_float2(scale, scale)) : acc;
     }
 #pragma unroll
-    for (int i = 0; i < 2 * M - 1; i++) { her[i] = er[B + i]; hei[i] = ei[B + i]; }
+    for (int i = 0; i < 2 * M - 1; i++) he[i] = e[B + i];
 #pragma unroll
-    for (int i = 0; i < M; i++) { hor_[i] = or_[B + i]; hoi[i] = oi[B + i]; }
+    for (int i = 0; i < M; i++) ho[i] = o[B + i];
   }
 };
 template <int B, int STAGE>
@@ -479,11 +476,8 @@ __global__ void __launch_bounds__(128, 3) cascade_kernel(CascadeParams p) {
   long long q_cap = qb + p.seg_len;
   if (DC == DC_ZSR && q_cap > p.dc_end) q_cap = p.dc_end;
 
-  float vr = 0.0f, vi = 0.0f;
-  if (DC == DC_SCAN && qb > 0) {
-    float2 v0 = p.v_seg[gid];
-    vr = v0.x; vi = v0.y;
-  }
+  float2 v = make_float2(0.0f, 0.0f);
+  if (DC == DC_SCAN && qb > 0) v = p.v_seg[gid];
   if (qb < 0) qb = 0;
   long long q_end = i_hi > i_lo ? i_hi * D : qb;
   if (DC == DC_ZSR && q_cap > q_end) q_end = q_cap;
@@ -505,14 +499,14 @@ __global__ void __launch_bounds__(128, 3) cascade_kernel(CascadeParams p) {
   sa.reset(); sb.reset(); sc.reset(); sd.reset();
 
   // arbitrary resampler state (A.5): output j goes with input floor(j step / 2^24)
-  float wr[13 + NO], wi[13 + NO];
-  float obr[4], obi[4];            // four outputs (one 32-byte sector) are gathered per store
+  float2 w[13 + NO];
+  float2 obuf[4];                  // four outputs (one 32-byte sector) are gathered per store
   unsigned phase = 0, j32 = 0;
   if (ARB) {
 #pragma unroll
-    for (int i = 0; i < 4; i++) obr[i] = obi[i] = 0.0f;
+    for (int i = 0; i < 4; i++) obuf[i] = make_float2(0.0f, 0.0f);
 #pragma unroll
-    for (int i = 0; i < 13 + NO; i++) wr[i] = wi[i] = 0.0f;
+    for (int i = 0; i < 13 + NO; i++) w[i] = make_float2(0.0f, 0.0f);
     if (i_lo > 0) {
       const unsigned long long num = (unsigned long long)i_lo << 24;
       const unsigned long long j = (num + p.step - 1) / p.step;
@@ -525,6 +519,7 @@ __global__ void __launch_bounds__(128, 3) cascade_kernel(CascadeParams p) {
   const unsigned dmask = (unsigned)p.dst_mask;
   const unsigned ob32 = (unsigned)ob;
   const float scale = p.scale;
+  const float2 nalpha = make_float2(-p.alpha, -p.alpha);
 
   Loader<SRC> ld;
   ld.template init<G>(p.src, s, qb);
@@ -536,27 +531,27 @@ __global__ void __launch_bounds__(128, 3) cascade_kernel(CascadeParams p) {
     float xr[G], xi[G];
     ld.template convert<G>(p.src, qb + (long long)it * G, it, cur, xr, xi);
     cur = nxt;
+    float2 x[G];
+#pragma unroll
+    for (int i = 0; i < G; i++) x[i] = make_float2(xr[i], xi[i]);
     if (DC == DC_ZSR) {
-      if (it == cap_it) p.sums[gid] = make_float2(vr, vi);
+      if (it == cap_it) p.sums[gid] = v;
     }
     if (DC != DC_NONE) {
 #pragma unroll
       for (int i = 0; i < G; i++) {
-        float yr = fmaf(-p.alpha, vr, xr[i]), yi = fmaf(-p.alpha, vi, xi[i]);
-        vr += yr; vi += yi;
-        xr[i] = yr; xi[i] = yi;
+        const float2 y = ffma2(nalpha, v, x[i]);   // y = x - alpha v ; v += y  (A.1)
+        v = fadd2(v, y);
+        x[i] = y;
       }
     }
     // half-band stages; the launch's scale rides on the last present stage
-    float ar[G / 2 > 0 ? G / 2 : 1], ai[G / 2 > 0 ? G / 2 : 1];
-    float br[G / 4 > 0 ? G / 4 : 1], bi[G / 4 > 0 ? G / 4 : 1];
-    float cr[G / 8 > 0 ? G / 8 : 1], ci[G / 8 > 0 ? G / 8 : 1];
-    float dr[G / 16 > 0 ? G / 16 : 1], di[G / 16 > 0 ? G / 16 : 1];
-    float* outr = xr; float* outi = xi;
-    if constexpr (MA > 0) { sa.run(p, xr, xi, ar, ai, NST == 1 ? scale : 1.0f); outr = ar; outi = ai; }
-    if constexpr (MB > 0) { sb.run(p, ar, ai, br, bi, NST == 2 ? scale : 1.0f); outr = br; outi = bi; }
-    if constexpr (MC > 0) { sc.run(p, br, bi, cr, ci, NST == 3 ? scale : 1.0f); outr = cr; outi = ci; }
-    if constexpr (MD > 0) { sd.run(p, cr, ci, dr, di, NST == 4 ? scale : 1.0f); outr = dr; outi = di; }
+    float2 a[G / 2 > 0 ? G / 2 : 1], b2[G / 4 > 0 ? G / 4 : 1], c[G / 8 > 0 ? G / 8 : 1], d[G / 16 > 0 ? G / 16 : 1];
+    float2* out = x;
+    if constexpr (MA > 0) { sa.template run<NST == 1>(p, x, a, scale); out = a; }
+    if constexpr (MB > 0) { sb.template run<NST == 2>(p, a, b2, scale); out = b2; }
+    if constexpr (MC > 0) { sc.template run<NST == 3>(p, b2, c, scale); out = c; }
+    if constexpr (MD > 0) { sd.template run<NST == 4>(p, c, d, scale); out = d; }
 
     const int o0 = it * NO;                       // local index of this iteration's first output
     const int lo = own_lo - o0, hi = own_hi - o0; // owned b are [lo, hi)
@@ -566,21 +561,21 @@ __global__ void __launch_bounds__(128, 3) cascade_kernel(CascadeParams p) {
         float2* d2 = dst + ((ob32 + (unsigned)o0) & dmask);
 #pragma unroll
         for (int b = 0; b < NO / 4; b++) {
-          const float f[8] = {outr[4 * b], outi[4 * b], outr[4 * b + 1], outi[4 * b + 1], outr[4 * b + 2], outi[4 * b + 2], outr[4 * b + 3], outi[4 * b + 3]};
+          const float f[8] = {out[4 * b].x, out[4 * b].y, out[4 * b + 1].x, out[4 * b + 1].y, out[4 * b + 2].x, out[4 * b + 2].y, out[4 * b + 3].x, out[4 * b + 3].y};
           stg256(d2 + 4 * b, f);
         }
       } else if (all && (NO % 2 == 0)) {
         float4* d4 = (float4*)(dst + ((ob32 + (unsigned)o0) & dmask));
 #pragma unroll
-        for (int b = 0; b < NO / 2; b++) d4[b] = make_float4(outr[2 * b], outi[2 * b], outr[2 * b + 1], outi[2 * b + 1]);
+        for (int b = 0; b < NO / 2; b++) d4[b] = make_float4(out[2 * b].x, out[2 * b].y, out[2 * b + 1].x, out[2 * b + 1].y);
       } else if (hi > 0 && lo < NO) {
 #pragma unroll
         for (int b = 0; b < NO; b++)
-          if (b >= lo && b < hi) dst[(ob32 + (unsigned)(o0 + b)) & dmask] = make_float2(outr[b], outi[b]);
+          if (b >= lo && b < hi) dst[(ob32 + (unsigned)(o0 + b)) & dmask] = out[b];
       }
     } else {
 #pragma unroll
-      for (int b = 0; b < NO; b++) { wr[13 + b] = outr[b]; wi[13 + b] = outi[b]; }
+      for (int b = 0; b < NO; b++) w[13 + b] = out[b];
       if (hi > 0 && lo < NO) {
 #pragma unroll
         for (int b = 0; b < NO; b++) {
@@ -590,22 +585,22 @@ __global__ void __launch_bounds__(128, 3) cascade_kernel(CascadeParams p) {
               const float4* row = (const float4*)(sbank + (phase >> (24 - p.bits)) * BANK_STRIDE);
               const float4 h0 = row[0], h1 = row[1], h2 = row[2], h3 = row[3];
               const float h[14] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w, h2.x, h2.y, h2.z, h2.w, h3.x, h3.y};
-              float yr = 0.0f, yi = 0.0f;
+              float2 y = make_float2(0.0f, 0.0f);
 #pragma unroll
-              for (int k = 0; k < 14; k++) { yr = fmaf(h[k], wr[13 + b - k], yr); yi = fmaf(h[k], wi[13 + b - k], yi); }
+              for (int k = 0; k < 14; k++) y = fma_tap(h[k], w[13 + b - k], y);
               const unsigned slot = j32 & 3u;
 #pragma unroll
               for (int sl = 0; sl < 4; sl++)
-                if (slot == (unsigned)sl) { obr[sl] = yr; obi[sl] = yi; }
+                if (slot == (unsigned)sl) obuf[sl] = y;
               if (slot == 3u) {
                 float2* d2 = dst + ((j32 - 3u) & dmask);
                 if (ob_first == 0u) {
-                  const float f[8] = {obr[0], obi[0], obr[1], obi[1], obr[2], obi[2], obr[3], obi[3]};
+                  const float f[8] = {obuf[0].x, obuf[0].y, obuf[1].x, obuf[1].y, obuf[2].x, obuf[2].y, obuf[3].x, obuf[3].y};
                   stg256(d2, f);
                 } else {
 #pragma unroll
                   for (int sl = 1; sl < 4; sl++)
-                    if ((unsigned)sl >= ob_first) d2[sl] = make_float2(obr[sl], obi[sl]);
+                    if ((unsigned)sl >= ob_first) d2[sl] = obuf[sl];
                   ob_first = 0u;
                 }
               }
@@ -617,7 +612,7 @@ __global__ void __launch_bounds__(128, 3) cascade_kernel(CascadeParams p) {
         }
       }
 #pragma unroll
-      for (int i = 0; i < 13; i++) { wr[i] = wr[NO + i]; wi[i] = wi[NO + i]; }
+      for (int i = 0; i < 13; i++) w[i] = w[NO + i];
     }
   }
   if (ARB) {   // outputs of an unfinished group of four
@@ -625,10 +620,10 @@ __global__ void __launch_bounds__(128, 3) cascade_kernel(CascadeParams p) {
     float2* d2 = dst + ((j32 - pend) & dmask);
 #pragma unroll
     for (int sl = 0; sl < 3; sl++)
-      if ((unsigned)sl >= ob_first && (unsigned)sl < pend) d2[sl] = make_float2(obr[sl], obi[sl]);
+      if ((unsigned)sl >= ob_first && (unsigned)sl < pend) d2[sl] = obuf[sl];
   }
   if (DC == DC_ZSR) {
-    if (cap_it >= n_it) p.sums[gid] = make_float2(vr, vi);
+    if (cap_it >= n_it) p.sums[gid] = v;
   }
 }
 
