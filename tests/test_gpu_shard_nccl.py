@@ -27,6 +27,14 @@ def _run(iq, device):
 
 
 def _worker(rank, world, port, q):
+    try:
+        _worker_body(rank, world, port, q)
+    except Exception as e:   # the parent must not sit out its queue timeout on a GPU box
+        import traceback
+        q.put(("error", "rank %d: %s\n%s" % (rank, e, traceback.format_exc())))
+
+
+def _worker_body(rank, world, port, q):
     import torch
     import torch.distributed as dist
 
@@ -44,10 +52,12 @@ def _worker(rank, world, port, q):
     pcm[:count] = torch.from_numpy(g["pcm"]).cuda()
     dem = torch.zeros((most, 16, ns), dtype=torch.float32, device="cuda")
     dem[:count] = torch.from_numpy(g["demod"]).cuda()
-    all_pcm = [torch.empty_like(pcm) for _ in range(world)]
+    pcm_b = pcm.view(torch.uint8)                     # NCCL has no int16 type: the s16 audio travels as bytes
+    all_pcm_b = [torch.empty_like(pcm_b) for _ in range(world)]
     all_dem = [torch.empty_like(dem) for _ in range(world)]
-    dist.all_gather(all_pcm, pcm)
+    dist.all_gather(all_pcm_b, pcm_b)
     dist.all_gather(all_dem, dem)
+    all_pcm = [t.view(torch.int16) for t in all_pcm_b]
     stats = shard.gather_stats({"streams": count, "samples": count * N}, device="cuda")
     if rank == 0:
         rows_p, rows_d = [], []
@@ -73,7 +83,12 @@ def test_two_gpu_shard_bitwise_equals_single_gpu():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    pcm2, dem2, ns2, stats = q.get(timeout=600)
+    got = q.get(timeout=300)
+    if got[0] == "error":
+        for p in procs:
+            p.kill()
+        pytest.fail(got[1])
+    pcm2, dem2, ns2, stats = got
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
