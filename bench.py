@@ -158,6 +158,33 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------
+def reference_binary_rate(cores):
+    """The UNMODIFIED reference program (oracle/_ref/sdr_pmr446_ref, built by oracle/ref.mk from /root/reference/src with
+    file-backed SoapySDR / RtAudio stand-ins) on `cores` processes, each on a 10 s capture at the ONE configuration it
+    supports: 1.024 Msps hard-coded, one squelch-selected channel demodulated.  Informational (another config than the
+    bench line); None when the binary was not built."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "sdr_pmr446_ref")
+    if not os.path.exists(exe):
+        return None
+    import tempfile
+    from sdr_pmr446_b200 import synth
+    n = 10_240_000
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "iq.cu8")
+        synth.make_cu8(synth.CaptureSpec(fs=1024000.0, carriers=synth.CFG1_CARRIERS), n, 446).tofile(path)
+        env = dict(os.environ, REF_IQ=path, REF_IQ_FMT="cu8")
+        t0 = time.perf_counter()
+        ps = [subprocess.Popen([exe, "-a", "1.0"], env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for _ in range(cores)]
+        ok = all(p.wait() == 0 for p in ps)
+        dt = time.perf_counter() - t0
+    if not ok:
+        return None
+    with open(os.path.join(ROOT, "oracle", "_ref", "LIQUID")) as f:
+        dsp = f.read().strip()
+    return {"value": cores * n / dt / 1e6, "unit": UNIT, "cores": cores, "config": "1.024 Msps cu8, 16 channels channelized, 1 demodulated (the reference's own operating point)",
+            "dsp_objects": "liquid-dsp" if dsp == "system" else "oracle restatement of liquid-dsp (liquid-dsp is not installed)", "wall_s": dt}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -176,7 +203,9 @@ def run_reference(args, rank, world):
             "data": "synthetic", "config": config_dict(args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "reference = CPU oracle port of the liquid-dsp chain (reference cannot be compiled here: liquid-dsp v1.7.0 absent)"}
+            "note": "reference = CPU oracle port of the liquid-dsp chain at the bench configuration (2.4 Msps, all 16 channels); the "
+                    "reference's own programs compile (oracle/ref.mk) but are hard-wired to 1.024 Msps / one demodulated channel: reference_binary",
+            "reference_binary": reference_binary_rate(cores)}
     emit(line)
 
 
