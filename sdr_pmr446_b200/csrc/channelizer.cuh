@@ -131,8 +131,10 @@ template <> struct TapState<false> {};
 
 // TAPS = the selector taps (mag_part / edge) are wanted: a separate instantiation, so that the throughput path carries
 // none of their registers.
-template <bool NCO_CONST, bool TAPS>
-__global__ void __launch_bounds__(128, 3) channelize16_kernel(ChanParams p, ChanTaps tp) {
+// PIPE = true: the next batch's staging loads sit in registers across phase B + C (168 registers, 3 blocks per SM);
+// PIPE = false: they are only PREFETCHED into L2 a batch ahead and loaded when staged (128 registers, 4 blocks per SM).
+template <bool NCO_CONST, bool TAPS, bool PIPE = false>
+__global__ void __launch_bounds__(128, (PIPE || TAPS) ? 3 : 4) channelize16_kernel(ChanParams p, ChanTaps tp) {
   __shared__ __align__(16) float2 ch_smem[4 * CH_SMEM_WARP];
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -284,9 +286,14 @@ __global__ void __launch_bounds__(128, 3) channelize16_kernel(ChanParams p, Chan
 #pragma unroll
     for (int i = 0; i < 8; i++) t[i] = *(const float4*)(res + ((j0_32 + (unsigned)(jb + 2 * lane + 64 * i)) & rmask));
   };
+  auto prefetch_l2 = [&](int b) {
+    const int jb = 512 * b + CH_HIST * 16;
+#pragma unroll
+    for (int i = 0; i < 8; i++) asm volatile("prefetch.global.L2 [%0];" ::"l"(res + ((j0_32 + (unsigned)(jb + 2 * lane + 64 * i)) & rmask)));
+  };
   bool ca_next = false;
   bool fast_next = any && steady(b_first, ca_next);
-  if (fast_next) issue_loads(b_first);
+  if (fast_next && PIPE) issue_loads(b_first);
   if (any && !stage_history_fast(b_first))
     for (int pp = 2 * lane; pp < CH_HIST * 16; pp += 64) stage_pair(pp, 512 * b_first, 0);   // history of the first batch
 
@@ -312,6 +319,7 @@ __global__ void __launch_bounds__(128, 3) channelize16_kernel(ChanParams p, Chan
     }
     // ---- staging: 32 new frames = 512 samples, 8 pairs per lane --------------------------------------------------------------
     if (fast) {
+      if (!PIPE) issue_loads(batch);
       if (corr_all) {
         const int rel_b = seg_rel0 + boff + CH_HIST * 16;
         float2 v0[8], e[8];
@@ -337,6 +345,7 @@ __global__ void __launch_bounds__(128, 3) channelize16_kernel(ChanParams p, Chan
       for (int i = 0; i < 8; i++) stage_pair(CH_HIST * 16 + 2 * lane + 64 * i, boff, 1);
     }
     __syncwarp();
+    if (!PIPE && batch < b_last) prefetch_l2(batch + 1);
     // ---- phase A: branch filters.  Frame kk of the batch sits in X frames kk .. kk + 25 (newest last) --------------------------
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
@@ -355,7 +364,7 @@ __global__ void __launch_bounds__(128, 3) channelize16_kernel(ChanParams p, Chan
     }
     __syncwarp();
     fast_next = batch < b_last && steady(batch + 1, ca_next);
-    if (fast_next) issue_loads(batch + 1);
+    if (fast_next && PIPE) issue_loads(batch + 1);
     // ---- phase B + C: lane = frame kk = 32 batch + lane ------------------------------------------------------------------------
     {
       float2 v[16];
@@ -395,10 +404,10 @@ __global__ void __launch_bounds__(128, 3) channelize16_kernel(ChanParams p, Chan
             ta.macc[c] += sqrtf(fmaf(y0.x, y0.x, y0.y * y0.y));
             ta.macc[c + 1] += sqrtf(fmaf(y1.x, y1.x, y1.y * y1.y));
           }
-          if (tp.edge) {
+          if (own && (kk == k_first || kk == k_last) && tp.edge) {   // one lane of one batch per call
             float2* e = tp.edge + ((long long)s * 16 + c) * 2;
-            if (own && kk == k_first) { e[0] = y0; e[2] = y1; }
-            if (own && kk == k_last) { e[1] = y0; e[3] = y1; }
+            if (kk == k_first) { e[0] = y0; e[2] = y1; }
+            if (kk == k_last) { e[1] = y0; e[3] = y1; }
           }
         }
       }

@@ -440,7 +440,9 @@ extern "C" int pmr446_batch_execute_device(pmr446_batch* b, const void* iq, long
     long long warps = (long long)S * cp.tiles;   // one warp per (stream, frame tile)
     unsigned blocks = (unsigned)((warps * 32 + 127) / 128);
     const bool taps = tp.mag_part || tp.edge;
-    if (b->nco_lut && !taps) channelize16_kernel<true, false><<<blocks, 128, 0, st>>>(cp, tp);
+    static const bool pipe_regs = getenv("PMR446_CH_PIPE") && atoi(getenv("PMR446_CH_PIPE")) == 1;   // tuning probe
+    if (b->nco_lut && !taps && pipe_regs) channelize16_kernel<true, false, true><<<blocks, 128, 0, st>>>(cp, tp);
+    else if (b->nco_lut && !taps) channelize16_kernel<true, false><<<blocks, 128, 0, st>>>(cp, tp);
     else if (b->nco_lut) channelize16_kernel<true, true><<<blocks, 128, 0, st>>>(cp, tp);
     else if (!taps) channelize16_kernel<false, false><<<blocks, 128, 0, st>>>(cp, tp);
     else channelize16_kernel<false, true><<<blocks, 128, 0, st>>>(cp, tp);
