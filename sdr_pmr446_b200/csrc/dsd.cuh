@@ -27,13 +27,12 @@ static __global__ void dsd_freqdem_kernel(const float2* res, long long res_strid
 
 // arbitrary resampler on a real ring (A.5): z[k] = sum_t pfb[idx_k][t] * fm[i_k - t],
 // i_k = floor(k*step / 2^24), idx_k = (k*step mod 2^24) >> (24 - bits).
-// One block = 256 consecutive outputs of one stream: their inputs and the filter bank (rows 20 floats apart, see
-// cascade_kernel) are staged in shared memory, so an output costs 4 LDS.128 + 14 LDS.32 + 14 FFMA.
+// One block = 256 consecutive outputs of one stream: their inputs are staged in shared memory, the bank rows (16 floats,
+// 64-byte aligned) come from global memory with four 128-bit loads.
 constexpr int DSD_XS = 576;   // inputs staged per block: enough for 256 outputs at any step <= 2^25
 static __global__ void __launch_bounds__(256) dsd_arb_kernel(const float* fm, long long fm_stride, long long fm_mask, float* z, long long z_stride,
                                                              long long z_mask, long long k0, long long k1, unsigned step, int bits, const float* pfb) {
   __shared__ float xs[DSD_XS];
-  __shared__ __align__(16) float bank[256 * 20];
   const int s = blockIdx.y;
   const long long kb = k0 + (long long)blockIdx.x * 256;
   const long long kend = kb + 256 < k1 ? kb + 256 : k1;
@@ -48,7 +47,6 @@ static __global__ void __launch_bounds__(256) dsd_arb_kernel(const float* fm, lo
       const long long n = i_first + c;
       xs[c] = n >= 0 ? f[n & fm_mask] : 0.0f;
     }
-    for (int i = threadIdx.x; i < (16 << bits); i += 256) bank[(i >> 4) * 20 + (i & 15)] = __ldg(pfb + i);
   }
   __syncthreads();
   const long long k = kb + threadIdx.x;
@@ -58,8 +56,10 @@ static __global__ void __launch_bounds__(256) dsd_arb_kernel(const float* fm, lo
   const unsigned idx = (unsigned)(ph & 0xffffffu) >> (24 - bits);
   float acc = 0.0f;
   if (staged) {
-    const float4* row = (const float4*)(bank + idx * 20);
-    const float4 h0 = row[0], h1 = row[1], h2 = row[2], h3 = row[3];
+    // the row straight from the (L1 / L2 resident, 16 KB) bank: a x1.92 resampler cycles through 25 of its 256 rows, and
+    // staging all of them per 256 outputs cost more than the filtering (0.32 ms per 1024-stream step)
+    const float4* row = (const float4*)(pfb + ((size_t)idx << 4));
+    const float4 h0 = __ldg(row), h1 = __ldg(row + 1), h2 = __ldg(row + 2), h3 = __ldg(row + 3);
     const float h[14] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w, h2.x, h2.y, h2.z, h2.w, h3.x, h3.y};
     const float* x = xs + (int)(i - i_first);
 #pragma unroll

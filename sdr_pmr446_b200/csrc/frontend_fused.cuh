@@ -35,7 +35,7 @@ struct FusedParams {
 };
 
 // one half-band decimator stage on pairs: out[o] = x_odd[o - M] + sum_{j < 2M} h[j] x_even[o - j]   (A.4)
-template <int M, int B, int STAGE>
+template <int M, int B>
 struct HbPair {
   float2 he[2 * M - 1], ho[M];   // previous even / odd samples, oldest first
   __device__ __forceinline__ void reset() {
@@ -47,7 +47,7 @@ struct HbPair {
   // SM: the history lives in the thread's shared-memory column (slot k at sm[k * FF_THREADS]) instead of he / ho, which
   // are then never touched: a stage that runs once per iteration only needs its window in registers while it runs
   template <bool SCALE, bool SM = false>
-  __device__ __forceinline__ void run(const CascadeParams& p, const float2* x, float2* y, float scale, float2* sm = nullptr) {
+  __device__ __forceinline__ void run(const float* h, const float2* x, float2* y, float scale, float2* sm = nullptr) {
     float2 e[2 * M - 1 + B], o[M + B];
 #pragma unroll
     for (int i = 0; i < 2 * M - 1; i++) e[i] = SM ? sm[i * FF_THREADS] : he[i];
@@ -59,7 +59,7 @@ struct HbPair {
     for (int b = 0; b < B; b++) {
       float2 acc = o[b];
 #pragma unroll
-      for (int j = 0; j < 2 * M; j++) acc = fma_tap(p.hb[STAGE][j], e[2 * M - 1 + b - j], acc);
+      for (int j = 0; j < 2 * M; j++) acc = fma_tap(h[j], e[2 * M - 1 + b - j], acc);   // h points into the kernel parameters
       y[b] = SCALE ? fmul2(acc, make_float2(scale, scale)) : acc;
     }
     if (SM) {
@@ -154,9 +154,9 @@ __global__ void __launch_bounds__(FF_THREADS, NB) fused_frontend_kernel(FusedPar
   int own_lo = (int)(i_lo - ob), own_hi = (int)(i_hi - ob);
   if (i_hi <= i_lo) own_lo = own_hi = 0;
 
-  HbPair<3, FF_SUB / 2, 0> sa;
-  HbPair<5, FF_SUB / 4, 1> sb;
-  HbPair<10, FF_G / 8, 2> sc;
+  HbPair<3, FF_SUB / 2> sa;
+  HbPair<5, FF_SUB / 4> sb;
+  HbPair<10, FF_G / 8> sc;
   sa.reset(); sb.reset(); sc.reset();
   float2 aw[13];                                                   // resampler window: previous 300 kHz samples, oldest first
 #pragma unroll
@@ -223,13 +223,13 @@ __global__ void __launch_bounds__(FF_THREADS, NB) fused_frontend_kernel(FusedPar
         }
       }
       float2 a[FF_SUB / 2], b[FF_SUB / 4];
-      sa.template run<false>(p, x, a, 1.0f);
-      sb.template run<false>(p, a, b, 1.0f);
+      sa.template run<false>(p.hb[0], x, a, 1.0f);
+      sb.template run<false>(p.hb[1], a, b, 1.0f);
 #pragma unroll
       for (int i = 0; i < 4; i++) cin[4 * sub + i] = b[i];
     }
     float2 c[6];                                                   // 300 kHz, scaled by 2^-3 like msresamp2 does
-    sc.template run<true, SMH>(p, cin, c, scale, smc);
+    sc.template run<true, SMH>(p.hb[2], cin, c, scale, smc);
     // arbitrary resampler (A.5), phase period 2: outputs 4 it + {0, 1, 2, 3} sit at local inputs 6 it + {0, 1, 3, 4}
     float2 w[13 + 6];
 #pragma unroll
@@ -269,6 +269,131 @@ __global__ void __launch_bounds__(FF_THREADS, NB) fused_frontend_kernel(FusedPar
       if (it == cap_it) p.sums[gid] = v;
     }
     if (3 * it >= ld.fast_lo && 3 * it + 2 < ld.fast_hi) iteration(it, std::true_type());
+    else iteration(it, std::false_type());
+  }
+  if (DC == DC_ZSR) {
+    if (cap_it >= n_it) p.sums[gid] = v;
+  }
+}
+
+// ---- front6_kernel: the first SIX half-band stages of a deep plan in one pass (dsd_in: 2.4 Msps -> 37.5 kHz, /root/reference/
+// src/dsd_in.c:167-168 with msresamp's stage list 3,3,3,3,3,5,10 or 3,3,3,3,5,10) -------------------------------------------------
+// Same structure as fused_frontend_kernel: iteration = 64 input samples = four 16-sample sub-blocks through cvt + DC + two m=3
+// stages, then 16 -> 8 -> 4 -> 2 -> 1 samples through the other four.  Replaces cascade_kernel<cu8, DC_ZSR, 16, 3,3,3,3> (whose
+// 16-sample iterations spend more instructions moving the late stages' windows than filtering) AND the launch after it.
+struct Front6Params {
+  CascadeParams c;      // c.hb[0..3] = taps of stages 1-4 (all m = 3)
+  float hb5[20], hb6[20];
+};
+constexpr int F6_G = 64, F6_D = 64;
+
+template <int DC, int ME, int MF>
+__global__ void __launch_bounds__(FF_THREADS, 2) front6_kernel(Front6Params fp) {
+  const CascadeParams& p = fp.c;
+  long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)p.n_streams * p.nseg) return;
+  const int s = (int)(gid / p.nseg), t = (int)(gid % p.nseg);
+  const long long T0 = p.seg0 + (long long)t * p.seg_len;
+  long long i_lo = T0 / F6_D, i_hi = (T0 + p.seg_len) / F6_D;
+  if (i_lo < p.out0) i_lo = p.out0;
+  if (i_hi > p.out1) i_hi = p.out1;
+  long long qb = T0 - p.halo;
+  long long q_cap = qb + p.seg_len;
+  if (DC == DC_ZSR && q_cap > p.dc_end) q_cap = p.dc_end;
+  if (qb < 0) qb = 0;
+  long long q_end = i_hi > i_lo ? i_hi * F6_D : qb;
+  if (DC == DC_ZSR && q_cap > q_end) q_end = q_cap;
+  if (q_end <= qb) {
+    if (DC == DC_ZSR) p.sums[gid] = make_float2(0.0f, 0.0f);
+    return;
+  }
+  const int n_it = (int)((q_end - qb + F6_G - 1) / F6_G);
+  const int cap_it = (DC == DC_ZSR) ? (q_cap > qb ? (int)((q_cap - qb) / F6_G) : 0) : -1;
+  const long long ob = qb / F6_D;
+  int own_lo = (int)(i_lo - ob), own_hi = (int)(i_hi - ob);
+  if (i_hi <= i_lo) own_lo = own_hi = 0;
+
+  HbPair<3, 8> sa;
+  HbPair<3, 4> sb;
+  HbPair<ME, 2> se;
+  HbPair<MF, 1> sf;
+  sa.reset(); sb.reset(); se.reset(); sf.reset();
+  float2 v = make_float2(0.0f, 0.0f);
+  float2* dst = p.dst + (long long)s * p.dst_stride;
+  const unsigned dmask = (unsigned)p.dst_mask, ob32 = (unsigned)ob;
+  const float scale = p.scale;
+  const float2 nalpha = make_float2(-p.alpha, -p.alpha), cpole = make_float2(1.0f - p.alpha, 1.0f - p.alpha);
+
+  Loader<SRC_CU8> ld;
+  ld.template init<FF_SUB>(p.src, s, qb);
+  const int n_sub = 4 * n_it;
+  Raw<SRC_CU8, FF_SUB> raw[4];
+  auto fetch = [&](int sbi, Raw<SRC_CU8, FF_SUB>& r) {
+    if (sbi >= ld.fast_lo && sbi < ld.fast_hi) ldg256_nc(ld.fp + (size_t)sbi * (2 * FF_SUB), r.w);
+  };
+  auto prefetch = [&](int sbi) {
+    if (sbi >= ld.fast_lo && sbi < ld.fast_hi) asm volatile("prefetch.global.L1 [%0];" ::"l"(ld.fp + (size_t)sbi * (2 * FF_SUB)));
+  };
+#pragma unroll
+  for (int i = 2; i < FF_PF; i++) prefetch(i);
+  fetch(0, raw[0]);
+  if (n_sub > 1) fetch(1, raw[1]);
+
+  HbPair<3, 4> sc4;   // stages 3 and 4 run per HALF iteration (32 inputs): shorter live ranges than 16-sample staging arrays
+  HbPair<3, 2> sd2;
+  sc4.reset(); sd2.reset();
+  auto iteration = [&](const int it, auto fast_tag) {
+    constexpr bool FAST = decltype(fast_tag)::value;
+    float2 d[4];
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      float2 cin[8];
+#pragma unroll
+      for (int s2 = 0; s2 < 2; s2++) {
+        const int sub = 2 * half + s2;
+        const int sbi = 4 * it + sub;
+        if (sbi + FF_PF < n_sub) prefetch(sbi + FF_PF);
+        if (sbi + 2 < n_sub) fetch(sbi + 2, raw[(sub + 2) % 4]);
+        float2 x[FF_SUB];
+        if (FAST) {
+#pragma unroll
+          for (int j = 0; j < FF_SUB / 2; j++) { x[2 * j] = cu8_pair(raw[sub].w[j], 0); x[2 * j + 1] = cu8_pair(raw[sub].w[j], 1); }
+        } else {
+          float xr[FF_SUB], xi[FF_SUB];
+          ld.template convert<FF_SUB>(p.src, qb + (long long)sbi * FF_SUB, sbi, raw[sub], xr, xi);
+#pragma unroll
+          for (int i = 0; i < FF_SUB; i++) x[i] = make_float2(xr[i], xi[i]);
+        }
+        if (DC != DC_NONE) {
+#pragma unroll
+          for (int i = 0; i < FF_SUB; i++) {
+            const float2 y = ffma2(nalpha, v, x[i]);
+            v = ffma2(cpole, v, x[i]);
+            x[i] = y;
+          }
+        }
+        float2 a[8], b[4];
+        sa.template run<false>(p.hb[0], x, a, 1.0f);
+        sb.template run<false>(p.hb[1], a, b, 1.0f);
+#pragma unroll
+        for (int i = 0; i < 4; i++) cin[4 * s2 + i] = b[i];
+      }
+      float2 c[4], dd[2];
+      sc4.template run<false>(p.hb[2], cin, c, 1.0f);
+      sd2.template run<false>(p.hb[3], c, dd, 1.0f);
+      d[2 * half] = dd[0];
+      d[2 * half + 1] = dd[1];
+    }
+    float2 e[2], f[1];
+    se.template run<false>(fp.hb5, d, e, 1.0f);
+    sf.template run<true>(fp.hb6, e, f, scale);
+    if (it >= own_lo && it < own_hi) dst[(ob32 + (unsigned)it) & dmask] = f[0];
+  };
+  for (int it = 0; it < n_it; it++) {
+    if (DC == DC_ZSR) {
+      if (it == cap_it) p.sums[gid] = v;
+    }
+    if (4 * it >= ld.fast_lo && 4 * it + 3 < ld.fast_hi) iteration(it, std::true_type());
     else iteration(it, std::false_type());
   }
   if (DC == DC_ZSR) {

@@ -25,13 +25,14 @@ struct Level {
   int src = SRC_RING;
   int dc = DC_NONE;
   bool arb = false;
-  int ms[4] = {0, 0, 0, 0};
+  int ms[6] = {0, 0, 0, 0, 0, 0};
   int nst = 0, D = 1, G = 16, unit = 16, halo = 0, seg_len = 1024;
-  float hb[4][20];
+  float hb[6][20];
   float scale = 1.0f;
   cascade_fn fn = nullptr;
   bool tile = false;      // last level runs hbarb_tile_kernel<10, 2, 3> instead of the segment-sequential cascade
   bool fused = false;     // the only level: fused_frontend_kernel (cu8 -> m = 3, 5, 10 -> resampler x 2/3) in one pass
+  bool front6 = false;    // level 0 of a deep plan: front6_kernel (cu8 -> six half-bands) in one pass
   float arb_rows[2][14];
   DevBuf ring;            // output ring [S][cap] float2
   long long cap = 0;
@@ -94,7 +95,8 @@ inline bool cut_groups(std::vector<int> order, std::vector<std::vector<int>>* gr
 struct Frontend {
   // How a plan is cut into launches (pure host logic, also exported through pmr446_describe_frontend for the CPU tests):
   // groups[0 .. n-2] are half-band groups, groups[n-1] is the resampler's launch (with the last half-band, or empty).
-  static int plan_groups(const design::MsresampPlan& plan, int in_fmt, std::vector<std::vector<int>>* groups, bool* fused) {
+  static int plan_groups(const design::MsresampPlan& plan, int in_fmt, std::vector<std::vector<int>>* groups, bool* fused, bool* front6 = nullptr) {
+    if (front6) *front6 = false;
     // execution-order stage list: plan.m[stages-1] runs first
     std::vector<int> order;
     for (int g = (int)plan.stages - 1; g >= 0; g--) order.push_back((int)plan.m[g]);
@@ -110,8 +112,16 @@ struct Frontend {
     const char* fe_env = getenv("PMR446_FRONTEND");
     *fused = in_fmt == PMR446_FMT_CU8 && order.size() == 3 && order[0] == 3 && order[1] == 5 && order[2] == 10 &&
              plan.step == (3u << 23) && !(fe_env && strcmp(fe_env, "split") == 0);
+    // deep cu8 plans (dsd_in: 3,3,3,3,3,5,10 at 2.4 Msps, 3,3,3,3,5,10 at 1.024 Msps): the first six stages in one launch
+    const bool six = front6 && in_fmt == PMR446_FMT_CU8 && (order.size() == 6 || order.size() == 7) && order[0] == 3 && order[1] == 3 &&
+                     order[2] == 3 && order[3] == 3 && ((order[4] == 3 && order[5] == 5) || (order[4] == 5 && order[5] == 10)) &&
+                     !(fe_env && strcmp(fe_env, "split") == 0);
     if (*fused) {
       groups->push_back(order);
+    } else if (six) {
+      *front6 = true;
+      groups->emplace_back(order.begin(), order.begin() + 6);
+      groups->emplace_back(order.begin() + 6, order.end());   // [10] + resampler, or the resampler alone
     } else {
       if (!order.empty() && !split_arb) { last.push_back(order.back()); order.pop_back(); }
       if (!cut_groups(order, groups)) return fail(PMR446_EINVAL, "resampler plan not built: unexpected half-band stage list");
@@ -207,8 +217,8 @@ struct Frontend {
     if (plan.step < (1u << 24)) return fail(PMR446_EINVAL, "internal: decimating plan with arbitrary rate > 1");
     if (plan.bits > 8) return fail(PMR446_EINVAL, "resampler filter bank larger than 256 rows");
     std::vector<std::vector<int>> groups;   // pre-launch groups, then the arb launch
-    bool want_fused = false;
-    if (int rc = plan_groups(plan, in_fmt, &groups, &want_fused)) return rc;
+    bool want_fused = false, want_front6 = false;
+    if (int rc = plan_groups(plan, in_fmt, &groups, &want_fused, &want_front6)) return rc;
     levels.resize(groups.size());
     long long max_in = max_chunk;
     int stage_cursor = (int)plan.stages - 1;  // index into plan.m / plan.hb of the next stage to place
@@ -216,6 +226,7 @@ struct Frontend {
       Level& L = levels[l];
       L.src = (l == 0) ? (in_fmt == PMR446_FMT_CU8 ? SRC_CU8 : SRC_CF32) : SRC_RING;
       L.fused = want_fused;
+      L.front6 = want_front6 && l == 0;
       L.dc = (l == 0 && dc) ? ((groups.size() >= 2 || L.fused) ? DC_ZSR : DC_SCAN) : DC_NONE;
       L.arb = (l + 1 == groups.size());
       L.nst = (int)groups[l].size();
@@ -231,8 +242,8 @@ struct Frontend {
       }
       if (L.arb) halo += 14 * L.D;
       L.scale = 1.0f / (float)L.D;
-      if (!L.fused) L.fn = pick_cascade(L.src, L.dc, L.arb, L.ms, &L.G);
-      if (!L.fn && !L.fused) {
+      if (!L.fused && !L.front6) L.fn = pick_cascade(L.src, L.dc, L.arb, L.ms, &L.G);
+      if (!L.fn && !L.fused && !L.front6) {
         char msg[160];
         snprintf(msg, sizeof msg, "resampler plan not built: level %zu src=%d dc=%d arb=%d stages=[%d,%d,%d,%d]", l, L.src, L.dc,
                  (int)L.arb, L.ms[0], L.ms[1], L.ms[2], L.ms[3]);
@@ -263,6 +274,12 @@ struct Frontend {
           const unsigned row = (unsigned)((((unsigned long long)r * plan.step) & ((1u << 24) - 1)) >> (24 - plan.bits));
           for (int k = 0; k < 14; k++) L.arb_rows[r][k] = plan.pfb[(size_t)row * plan.sub_len + k];
         }
+      }
+      if (L.front6) {   // long segments: the warm-up of six stages is 1024 samples
+        L.G = F6_G;
+        int sl = 16384;
+        while (sl > 4096 && (long long)S * ((max_in + sl - 1) / sl) < 148LL * 256) sl >>= 1;
+        L.seg_len = std::max(sl, seg_min);
       }
       if (L.arb && !L.fused) {
         // equal resampler phase at every segment start (all lanes of a warp then emit outputs in
@@ -456,6 +473,38 @@ struct Frontend {
           *launches += 1;
           tm->mark(st, TM_CASCADE0 + (int)std::min<size_t>(l, 2));
           new_out = j1;
+        }
+      } else if (L.front6) {
+        if (out1 > out0 || (L.dc == DC_ZSR && nseg > 0)) {
+          Front6Params fp;
+          memset(&fp, 0, sizeof fp);
+          CascadeParams& cp = fp.c;
+          cp.src = sv;
+          cp.n_streams = S;
+          cp.nseg = nseg;
+          cp.seg0 = seg0;
+          cp.seg_len = L.seg_len;
+          cp.halo = L.halo;
+          cp.out0 = out0;
+          cp.out1 = out1;
+          cp.scale = L.scale;
+          cp.alpha = alpha_eff;
+          cp.sums = (float2*)sums.p;
+          cp.dc_end = seg0_next - L.halo;
+          cp.dst = (float2*)L.ring.p;
+          cp.dst_stride = L.cap;
+          cp.dst_mask = L.cap - 1;
+          memcpy(cp.hb, L.hb, sizeof cp.hb);
+          memcpy(fp.hb5, L.hb[4], sizeof fp.hb5);
+          memcpy(fp.hb6, L.hb[5], sizeof fp.hb6);
+          const bool e3 = L.ms[4] == 3;
+          if (L.dc == DC_ZSR && e3) front6_kernel<DC_ZSR, 3, 5><<<blocks, FF_THREADS, 0, st>>>(fp);
+          else if (L.dc == DC_ZSR) front6_kernel<DC_ZSR, 5, 10><<<blocks, FF_THREADS, 0, st>>>(fp);
+          else if (e3) front6_kernel<DC_NONE, 3, 5><<<blocks, FF_THREADS, 0, st>>>(fp);
+          else front6_kernel<DC_NONE, 5, 10><<<blocks, FF_THREADS, 0, st>>>(fp);
+          *launches += 1;
+          tm->mark(st, TM_CASCADE0);
+          if (out1 > out0) new_out = out1;
         }
       } else if (L.fused) {
         if (out1 > out0 || (L.dc == DC_ZSR && nseg > 0)) {

@@ -752,8 +752,8 @@ extern "C" int pmr446_describe_frontend(float rate, float as, int in_fmt, int wi
   if (rate > 1.0f) return fail(PMR446_EINVAL, "front end only decimates (rate <= 1)");
   design::MsresampPlan p = design::msresamp_plan(rate, as);
   std::vector<std::vector<int>> groups;
-  bool fused = false;
-  if (int rc = Frontend::plan_groups(p, in_fmt, &groups, &fused)) return rc;
+  bool fused = false, front6 = false;
+  if (int rc = Frontend::plan_groups(p, in_fmt, &groups, &fused, &front6)) return rc;
   std::string out;
   for (size_t l = 0; l < groups.size(); l++) {
     const bool arb = l + 1 == groups.size();
@@ -762,9 +762,10 @@ extern "C" int pmr446_describe_frontend(float rate, float as, int in_fmt, int wi
     int ms[4] = {0, 0, 0, 0}, G = 0;
     for (size_t k = 0; k < groups[l].size() && k < 4; k++) ms[k] = groups[l][k];
     const bool tile = arb && src == SRC_RING && groups[l].size() == 1 && ms[0] == 10 && p.step == (3u << 23);
-    if (!fused && !tile && !pick_cascade(src, dc, arb, ms, &G)) return fail(PMR446_EINVAL, "resampler plan not built: kernel not instantiated");
+    const bool f6 = front6 && l == 0;
+    if (!fused && !tile && !f6 && !pick_cascade(src, dc, arb, ms, &G)) return fail(PMR446_EINVAL, "resampler plan not built: kernel not instantiated");
     if (l) out += " | ";
-    out += fused ? "fused[" : (tile ? "tile[" : "cascade[");
+    out += fused ? "fused[" : (f6 ? "front6[" : (tile ? "tile[" : "cascade["));
     for (size_t k = 0; k < groups[l].size(); k++) out += (k ? "," : "") + std::to_string(groups[l][k]);
     out += arb ? "]+arb" : "]";
   }

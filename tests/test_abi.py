@@ -163,7 +163,8 @@ def test_every_decimating_rate_has_a_frontend_plan():
     assert plan(2400000, 200000, 1) == "fused[3,5,10]+arb"                       # configs[2]: one launch
     assert plan(2400000, 200000, 0) == "cascade[3,5] | tile[10]+arb"
     assert plan(1024000, 200000, 1) == "cascade[5,10] | cascade[]+arb"           # configs[0]
-    assert plan(2400000, 12500, 1) == "cascade[3,3,3,3] | cascade[3,5] | tile[10]+arb"   # configs[1]
+    assert plan(2400000, 12500, 1) == "front6[3,3,3,3,3,5] | tile[10]+arb"             # configs[1]: six half-bands in one launch
+    assert plan(1024000, 12500, 1) == "front6[3,3,3,3,5,10] | cascade[]+arb"           # dsd_in at the reference's own rate
     assert plan(20000000, 20000000, 0) == "cascade[]+arb"                        # configs[3]: rate 1.0
     assert plan(3200000, 200000, 1) == "cascade[3,5] | cascade[10]+arb"
     rng = np.random.default_rng(7)
