@@ -14,8 +14,8 @@
 //   register window, all 26 taps in registers, one packed FFMA2 per complex tap (scalar-broadcast operand); two passes
 //   cover the lane's 16 frames.  The commutator sends resampled sample 16 f + 15 - i to branch i; the dot product of
 //   frame f goes to shared memory row f, column n = 15 - i (the DFT input index).
-//  Phase B + C: lane = frame: 16-point forward DFT in registers, the previous frame's channel values by shuffle (lane 0
-//   takes the last frame of the previous batch from shared memory), discriminator arg(conj(y[f-1]) y[f]) with a polynomial
+//  Phase B + C: lane = frame: 16-point forward DFT in registers, the channel values go back to the lane's shared-memory row
+//   and the previous frame's are read from the row before it (row -1 = the last frame of the previous batch), discriminator arg(conj(y[f-1]) y[f]) with a polynomial
 //   atan2 (|err| < 3e-7 rad), and for every channel ONE coalesced 128-byte store of 32 consecutive frames into the
 //   channel's ring row -- no transpose pass.
 // Frame 0 of a tile only provides the "previous frame" of frame 1, so a tile owns 159 frames.
@@ -57,7 +57,9 @@ constexpr int CH_TL = CH_FR - 1;              // owned frames per tile
 constexpr int CH_HIST = 25;                   // frames of branch-filter history in front of a batch (26 taps)
 constexpr int CH_XN = (CH_HIST + 32) * 16;    // float2 per sample buffer: 57 frames
 constexpr int CH_V_STRIDE = 17;               // float2 per frame row of the branch-output buffer (16 + 1 pad)
-constexpr int CH_SMEM_WARP = CH_XN + 32 * CH_V_STRIDE + 16;   // + the previous batch's last frame (16 channels)
+constexpr int CH_SMEM_WARP = CH_XN + 33 * CH_V_STRIDE + 1;    // 33 rows (row 0 = the previous batch's last frame); even: the
+                                                              // sample buffers of all four warps stay 16-byte aligned
+static_assert(CH_SMEM_WARP % 2 == 0 && CH_XN % 2 == 0, "128-bit shared-memory accesses need 16-byte aligned warp slices");
 
 // atan2 by a degree-17 odd minimax polynomial on [0, 1] (Abramowitz & Stegun 4.4.49, |err| <= 2e-8 in
 // exact arithmetic, < 3e-7 rad in float32); (0, 0) falls back to libm for the signed-zero cases.
@@ -140,8 +142,8 @@ __global__ void __launch_bounds__(128, (PIPE || TAPS) ? 3 : 4) channelize16_kern
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp >= (long long)p.n_streams * p.tiles) return;   // warp-uniform
   float2* const X = ch_smem + (threadIdx.x >> 5) * CH_SMEM_WARP;   // [57 frames][16 samples], mixed
-  float2* const V = X + CH_XN;                                     // [32 frames][17]: branch outputs, column = DFT input index
-  float2* const carry = V + 32 * CH_V_STRIDE;                      // [16] channel values of the previous batch's last frame
+  float2* const V = X + CH_XN + CH_V_STRIDE;                       // [-1 .. 31 frames][17]: branch outputs (column = DFT input index), then
+                                                                   // channel values; row -1 = the previous batch's last frame
   const int s = (int)(warp / p.tiles);
   const int tile_idx = (int)(warp % p.tiles);
   const long long fa = (p.tile0 + tile_idx) * CH_TL, fs = fa - 1;  // computed frames are fs + k, k in [0, 160)
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(128, (PIPE || TAPS) ? 3 : 4) channelize16_kern
   const bool any = own_hi > own_lo;             // (every launched tile owns a frame; kept warp-uniform and safe anyway)
   const int b_first = any ? (own_lo - 1) / 32 : 0, b_last = any ? (own_hi - 1) / 32 : -1;
 
-  if (lane < 16) carry[lane] = make_float2(0.0f, 0.0f);
+  if (lane < 16) V[-CH_V_STRIDE + lane] = make_float2(0.0f, 0.0f);
 
   // steady-state staging (warp-uniform per batch): every new sample of the batch exists and they all take the same
   // correction path.  Then the batch's eight 128-bit loads per lane are issued one batch AHEAD -- after phase A of the
@@ -367,55 +369,68 @@ __global__ void __launch_bounds__(128, (PIPE || TAPS) ? 3 : 4) channelize16_kern
     if (fast_next && PIPE) issue_loads(batch + 1);
     // ---- phase B + C: lane = frame kk = 32 batch + lane ------------------------------------------------------------------------
     {
+      float2* const row = V + lane * CH_V_STRIDE;
       float2 v[16];
 #pragma unroll
-      for (int n = 0; n < 16; n++) v[n] = V[lane * CH_V_STRIDE + n];
+      for (int n = 0; n < 16; n++) v[n] = row[n];
       dft16p(v);
+      // channel values back into the lane's own row (natural channel order): the next lane's "previous frame"
+#pragma unroll
+      for (int c = 0; c < 16; c++) row[c] = v[af_dig(c)];
+      __syncwarp();
       const int kk = 32 * batch + lane;
       const bool own = kk >= own_lo && kk < own_hi;
-      float* dptr = drow0 + ((fs32 + (unsigned)kk) & dmask);          // channel c lives demod_stride further per channel
-      float2* cptr = crow0 ? crow0 + (crel + kk) : nullptr;
+      const float2* prow = row - CH_V_STRIDE;                    // lane 0: row -1, the previous batch's last frame
+      float dm[16];
 #pragma unroll
       for (int c = 0; c < 16; c += 2) {
         const float2 y0 = v[af_dig(c)], y1 = v[af_dig(c + 1)];
-        float2 p0, p1;
-        p0.x = __shfl_up_sync(0xffffffffu, y0.x, 1); p0.y = __shfl_up_sync(0xffffffffu, y0.y, 1);
-        p1.x = __shfl_up_sync(0xffffffffu, y1.x, 1); p1.y = __shfl_up_sync(0xffffffffu, y1.y, 1);
-        if (lane == 0) { p0 = carry[c]; p1 = carry[c + 1]; }
-        if (kk == k_zero) { p0 = make_float2(0.0f, 0.0f); p1 = make_float2(0.0f, 0.0f); }
+        const float2 p0 = prow[c], p1 = prow[c + 1];
         // arg(conj(prev) y) with separate mul / add like the C reference (A.9)
         const float re0 = __fadd_rn(__fmul_rn(p0.x, y0.x), __fmul_rn(p0.y, y0.y));
         const float im0 = __fsub_rn(__fmul_rn(p0.x, y0.y), __fmul_rn(p0.y, y0.x));
         const float re1 = __fadd_rn(__fmul_rn(p1.x, y1.x), __fmul_rn(p1.y, y1.y));
         const float im1 = __fsub_rn(__fmul_rn(p1.x, y1.y), __fmul_rn(p1.y, y1.x));
         const float2 a = fast_atan2f_x2(im0, re0, im1, re1);
-        if (own) {
-          dptr[0] = a.x * p.ref;
-          dptr[p.demod_stride] = a.y * p.ref;
-          if (cptr) {
-            cptr[0] = y0;
-            cptr[p.chan_ld] = y1;
-          }
-        }
-        dptr += 2 * p.demod_stride;
-        if (cptr) cptr += 2 * p.chan_ld;
-        if constexpr (TAPS) {
-          if (own) {
-            ta.macc[c] += sqrtf(fmaf(y0.x, y0.x, y0.y * y0.y));
-            ta.macc[c + 1] += sqrtf(fmaf(y1.x, y1.x, y1.y * y1.y));
-          }
-          if (own && (kk == k_first || kk == k_last) && tp.edge) {   // one lane of one batch per call
-            float2* e = tp.edge + ((long long)s * 16 + c) * 2;
-            if (kk == k_first) { e[0] = y0; e[2] = y1; }
-            if (kk == k_last) { e[1] = y0; e[3] = y1; }
-          }
-        }
+        dm[c] = a.x * p.ref;
+        dm[c + 1] = a.y * p.ref;
       }
-      __syncwarp();   // lane 0 has read the previous batch's last frame
-      if (lane == 31) {
+      if (kk == k_zero) {   // absolute frame 0 (one lane, once per stream): r_prime = +0 + 0i exactly as the reference starts
 #pragma unroll
-        for (int c = 0; c < 16; c++) carry[c] = v[af_dig(c)];
+        for (int c = 0; c < 16; c++) {
+          const float2 y = v[af_dig(c)];
+          const float re = __fadd_rn(__fmul_rn(0.0f, y.x), __fmul_rn(0.0f, y.y));
+          const float im = __fsub_rn(__fmul_rn(0.0f, y.y), __fmul_rn(0.0f, y.x));
+          dm[c] = fast_atan2f(im, re) * p.ref;
+        }
       }
+      if (own) {
+        float* dptr = drow0 + ((fs32 + (unsigned)kk) & dmask);          // channel c lives demod_stride further per channel
+#pragma unroll
+        for (int c = 0; c < 16; c++) { *dptr = dm[c]; dptr += p.demod_stride; }
+        if (crow0) {
+          float2* cptr = crow0 + (crel + kk);
+#pragma unroll
+          for (int c = 0; c < 16; c++) { *cptr = v[af_dig(c)]; cptr += p.chan_ld; }
+        }
+        if constexpr (TAPS) {
+#pragma unroll
+          for (int c = 0; c < 16; c++) {
+            const float2 y = v[af_dig(c)];
+            ta.macc[c] += sqrtf(fmaf(y.x, y.x, y.y * y.y));
+          }
+          if ((kk == k_first || kk == k_last) && tp.edge) {   // one lane of one batch per call
+            float2* e = tp.edge + (long long)s * 32;
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+              if (kk == k_first) e[2 * c] = v[af_dig(c)];
+              if (kk == k_last) e[2 * c + 1] = v[af_dig(c)];
+            }
+          }
+        }
+      }
+      __syncwarp();   // every lane has read its previous frame
+      if (lane < 16) V[-CH_V_STRIDE + lane] = V[31 * CH_V_STRIDE + lane];
     }
   }
   if constexpr (TAPS) {

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) probe(float* out, int iters, Taps tp, flo
 }
 
 template <int MODE>
-static void run(const char* name, int sms) {
+static void run(const char* name, int sms, int blocks_per_sm = 8) {
   float* d;
   cudaMalloc(&d, 4);
   cudaEvent_t e0, e1;
@@ -49,7 +49,7 @@ static void run(const char* name, int sms) {
   cudaEventCreate(&e1);
   Taps tp;
   for (int i = 0; i < 16; i++) tp.h[i] = 0.999f - 0.0001f * i;
-  const int iters = 2048, blocks = sms * 8;
+  const int iters = 2048, blocks = sms * blocks_per_sm;
   double best = 0.0;
   for (int rep = 0; rep < 4; rep++) {
     cudaEventRecord(e0);
@@ -62,7 +62,7 @@ static void run(const char* name, int sms) {
     const double tf = 2.0 * fma / (ms * 1e-3) / 1e12;
     if (rep > 0 && tf > best) best = tf;
   }
-  printf("{\"mode\": \"%s\", \"tflops\": %.2f}\n", name, best);
+  printf("{\"mode\": \"%s\", \"warps_per_scheduler\": %d, \"tflops\": %.2f}\n", name, blocks_per_sm * 2, best);
   cudaFree(d);
 }
 
@@ -77,5 +77,7 @@ int main() {
   run<4>("ffma2_uniform_tap+1prmt", sms);
   run<5>("2ffma_const_tap+1prmt", sms);
   run<6>("ffma2_uniform_tap+prmt+iadd", sms);
+  // occupancy sweep: 256-thread blocks, 1 / 2 / 4 per SM = 2 / 4 / 8 warps per scheduler
+  for (int b = 1; b <= 4; b *= 2) { run<1>("ffma_const_tap", sms, b); run<3>("ffma2_uniform_tap", sms, b); run<4>("ffma2_uniform_tap+1prmt", sms, b); }
   return cudaDeviceSynchronize() != cudaSuccess;
 }
