@@ -293,8 +293,11 @@ __global__ void __launch_bounds__(128, (PIPE || TAPS) ? 3 : 4) channelize16_kern
 #pragma unroll
     for (int i = 0; i < 8; i++) asm volatile("prefetch.global.L2 [%0];" ::"l"(res + ((j0_32 + (unsigned)(jb + 2 * lane + 64 * i)) & rmask)));
   };
-  bool ca_next = false;
+  // steady() is monotone in the batch index, so a tile whose first and last batch are steady with the same correction
+  // mode (almost every tile) needs no per-batch evaluation
+  bool ca_next = false, ca_last = false;
   bool fast_next = any && steady(b_first, ca_next);
+  const bool tile_steady = fast_next && steady(b_last, ca_last) && ca_last == ca_next;
   if (fast_next && PIPE) issue_loads(b_first);
   if (any && !stage_history_fast(b_first))
     for (int pp = 2 * lane; pp < CH_HIST * 16; pp += 64) stage_pair(pp, 512 * b_first, 0);   // history of the first batch
@@ -365,7 +368,7 @@ __global__ void __launch_bounds__(128, (PIPE || TAPS) ? 3 : 4) channelize16_kern
       }
     }
     __syncwarp();
-    fast_next = batch < b_last && steady(batch + 1, ca_next);
+    fast_next = batch < b_last && (tile_steady || steady(batch + 1, ca_next));
     if (fast_next && PIPE) issue_loads(batch + 1);
     // ---- phase B + C: lane = frame kk = 32 batch + lane ------------------------------------------------------------------------
     {
