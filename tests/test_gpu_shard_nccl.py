@@ -84,7 +84,7 @@ def test_two_gpu_shard_bitwise_equals_single_gpu():
     for p in procs:
         p.start()
     got = q.get(timeout=300)
-    if got[0] == "error":
+    if isinstance(got[0], str):
         for p in procs:
             p.kill()
         pytest.fail(got[1])
