@@ -29,19 +29,20 @@ static __global__ void dsd_freqdem_kernel(const float2* res, long long res_strid
 // i_k = floor(k*step / 2^24), idx_k = (k*step mod 2^24) >> (24 - bits).
 // One block = 256 consecutive outputs of one stream: their inputs are staged in shared memory, the bank rows (16 floats,
 // 64-byte aligned) come from global memory with four 128-bit loads.
-constexpr int DSD_XS = 576;   // inputs staged per block: enough for 256 outputs at any step <= 2^25
+constexpr int DSD_XS = 1216;  // inputs staged per block: enough for 1024 outputs at any step >= 2^23 (rate <= 2), 4.9 KB
+constexpr int DSD_RB = 4;     // outputs per thread: a block of 256 threads covers 1024 consecutive outputs
 static __global__ void __launch_bounds__(256) dsd_arb_kernel(const float* fm, long long fm_stride, long long fm_mask, float* z, long long z_stride,
                                                              long long z_mask, long long k0, long long k1, unsigned step, int bits, const float* pfb) {
   __shared__ float xs[DSD_XS];
   const int s = blockIdx.y;
-  const long long kb = k0 + (long long)blockIdx.x * 256;
-  const long long kend = kb + 256 < k1 ? kb + 256 : k1;
+  const long long kb = k0 + (long long)blockIdx.x * (256 * DSD_RB);
+  const long long kend = kb + 256 * DSD_RB < k1 ? kb + 256 * DSD_RB : k1;
   if (kb >= k1) return;
   const float* f = fm + (long long)s * fm_stride;
   const long long i_first = (long long)(((unsigned long long)kb * step) >> 24) - 13;
   const long long i_last = (long long)(((unsigned long long)(kend - 1) * step) >> 24);
   const int count = (int)(i_last - i_first + 1);
-  const bool staged = count <= DSD_XS && bits <= 8;   // block-uniform
+  const bool staged = count <= DSD_XS;   // block-uniform
   if (staged) {
     for (int c = threadIdx.x; c < count; c += 256) {
       const long long n = i_first + c;
@@ -49,31 +50,32 @@ static __global__ void __launch_bounds__(256) dsd_arb_kernel(const float* fm, lo
     }
   }
   __syncthreads();
-  const long long k = kb + threadIdx.x;
-  if (k >= kend) return;
-  const unsigned long long ph = (unsigned long long)k * step;
-  const long long i = (long long)(ph >> 24);
-  const unsigned idx = (unsigned)(ph & 0xffffffu) >> (24 - bits);
-  float acc = 0.0f;
-  if (staged) {
-    // the row straight from the (L1 / L2 resident, 16 KB) bank: a x1.92 resampler cycles through 25 of its 256 rows, and
-    // staging all of them per 256 outputs cost more than the filtering (0.32 ms per 1024-stream step)
+#pragma unroll
+  for (int r = 0; r < DSD_RB; r++) {
+    const long long k = kb + threadIdx.x + 256 * r;
+    if (k >= kend) break;
+    const unsigned long long ph = (unsigned long long)k * step;
+    const long long i = (long long)(ph >> 24);
+    const unsigned idx = (unsigned)(ph & 0xffffffu) >> (24 - bits);
+    // the row straight from the (L1 / L2 resident, 16 KB) bank: a x1.92 resampler cycles through 25 of its 256 rows
     const float4* row = (const float4*)(pfb + ((size_t)idx << 4));
     const float4 h0 = __ldg(row), h1 = __ldg(row + 1), h2 = __ldg(row + 2), h3 = __ldg(row + 3);
     const float h[14] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w, h2.x, h2.y, h2.z, h2.w, h3.x, h3.y};
-    const float* x = xs + (int)(i - i_first);
+    float acc = 0.0f;
+    if (staged) {
+      const float* x = xs + (int)(i - i_first);
 #pragma unroll
-    for (int t = 0; t < 14; t++) acc = fmaf(h[t], x[-t], acc);
-  } else {
-    const float* row = pfb + ((size_t)idx << 4);
+      for (int t = 0; t < 14; t++) acc = fmaf(h[t], x[-t], acc);
+    } else {
 #pragma unroll
-    for (int t = 0; t < 14; t++) {
-      const long long n = i - t;
-      const float v = n >= 0 ? f[n & fm_mask] : 0.0f;
-      acc = fmaf(__ldg(row + t), v, acc);
+      for (int t = 0; t < 14; t++) {
+        const long long n = i - t;
+        const float v = n >= 0 ? f[n & fm_mask] : 0.0f;
+        acc = fmaf(h[t], v, acc);
+      }
     }
+    z[(long long)s * z_stride + (k & z_mask)] = acc;
   }
-  z[(long long)s * z_stride + (k & z_mask)] = acc;
 }
 
 // half-band interpolator (A.4) + s16: out[2k] = z[k - m], out[2k+1] = sum_j h[j] z[k - j]

@@ -137,7 +137,8 @@ extern "C" int dsd446_batch_execute_device(dsd446_batch* b, const void* iq, long
   }
   if (k1 > k0) {                                              // :170-175
     dim3 g((unsigned)((k1 - k0 + 255) / 256), S);
-    dsd_arb_kernel<<<g, 256, 0, st>>>((const float*)b->d_fm.p, b->fm_cap, b->fm_cap - 1, (float*)b->d_z.p, b->z_cap, b->z_cap - 1, k0, k1,
+    dim3 ga((unsigned)((k1 - k0 + 256 * DSD_RB - 1) / (256 * DSD_RB)), S);
+    dsd_arb_kernel<<<ga, 256, 0, st>>>((const float*)b->d_fm.p, b->fm_cap, b->fm_cap - 1, (float*)b->d_z.p, b->z_cap, b->z_cap - 1, k0, k1,
                                       b->up.step, (int)b->up.bits, (const float*)b->d_pfb_up.p);
     DsdInterpParams ip;
     ip.z = (const float*)b->d_z.p;
