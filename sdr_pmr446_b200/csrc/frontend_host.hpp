@@ -65,6 +65,11 @@ inline cascade_fn pick_cascade(int src, int dc, bool arb, const int* ms, int* G)
   } else {
     if (dc == DC_NONE && src == SRC_RING && is(10, 0, 0, 0)) { *G = 8; return cfn<SRC_RING, DC_NONE, 8, 10, 0, 0, 0, true>(); }
     if (dc == DC_NONE && src == SRC_RING && is(0, 0, 0, 0)) { *G = 8; return cfn<SRC_RING, DC_NONE, 8, 0, 0, 0, 0, true>(); }
+    // [5, 10] + dynamic-phase resampler in ONE launch (1.024 Msps -> 200 kHz, the reference's own plan): the DC blocker's
+    // state per segment comes from a pre-pass over the raw input (DC_SCAN: +2 GB read), which is cheaper than the 256 kHz
+    // ring round trip and the second launch it replaces
+    if (dc == DC_SCAN && src == SRC_CU8 && is(5, 10, 0, 0)) return cfn<SRC_CU8, DC_SCAN, 16, 5, 10, 0, 0, true>();
+    if (dc == DC_SCAN && src == SRC_CF32 && is(5, 10, 0, 0)) return cfn<SRC_CF32, DC_SCAN, 16, 5, 10, 0, 0, true>();
     if (dc == DC_SCAN && src == SRC_CU8 && is(0, 0, 0, 0)) return cfn<SRC_CU8, DC_SCAN, 16, 0, 0, 0, 0, true>();
     if (dc == DC_SCAN && src == SRC_CF32 && is(0, 0, 0, 0)) return cfn<SRC_CF32, DC_SCAN, 16, 0, 0, 0, 0, true>();
     if (dc == DC_NONE && src == SRC_CF32 && is(0, 0, 0, 0)) return cfn<SRC_CF32, DC_NONE, 16, 0, 0, 0, 0, true>();
@@ -95,7 +100,8 @@ inline bool cut_groups(std::vector<int> order, std::vector<std::vector<int>>* gr
 struct Frontend {
   // How a plan is cut into launches (pure host logic, also exported through pmr446_describe_frontend for the CPU tests):
   // groups[0 .. n-2] are half-band groups, groups[n-1] is the resampler's launch (with the last half-band, or empty).
-  static int plan_groups(const design::MsresampPlan& plan, int in_fmt, std::vector<std::vector<int>>* groups, bool* fused, bool* front6 = nullptr) {
+  static int plan_groups(const design::MsresampPlan& plan, int in_fmt, std::vector<std::vector<int>>* groups, bool* fused, bool* front6 = nullptr,
+                         bool with_dc_hint = true) {
     if (front6) *front6 = false;
     // execution-order stage list: plan.m[stages-1] runs first
     std::vector<int> order;
@@ -107,6 +113,11 @@ struct Frontend {
     // m = 10 window.  A single half-band also runs on its own (the resampler kernel with a half-band only reads a ring).
     // Otherwise the last half-band goes with the resampler (tiled kernel when the phase has period 2).
     const bool split_arb = (order.size() == 2 && order[0] == 5 && order[1] == 10 && plan.step != (3u << 23)) || order.size() == 1;
+    // PMR446_FRONTEND=one runs that plan as ONE launch instead (DC pre-pass + [5, 10] + resampler, see pick_cascade): measured
+    // 0.57 + 2.34 ms against 1.35 + 1.14 ms for the two launches at 1024 x 1.024 Msps, so it is not the default
+    const char* fe_env0 = getenv("PMR446_FRONTEND");
+    const bool one_launch = order.size() == 2 && order[0] == 5 && order[1] == 10 && plan.step != (3u << 23) && with_dc_hint &&
+                            fe_env0 && strcmp(fe_env0, "one") == 0;
     // 2.4 Msps cu8 -> 200 kHz ([3, 5, 10] + rate 2/3): everything in ONE launch, no intermediate ring (frontend_fused.cuh).
     // PMR446_FRONTEND=split keeps round 1's two launches (cascade -> 600 kHz ring -> tiled half-band + resampler) for A/B runs.
     const char* fe_env = getenv("PMR446_FRONTEND");
@@ -118,6 +129,8 @@ struct Frontend {
                      !(fe_env && strcmp(fe_env, "split") == 0);
     if (*fused) {
       groups->push_back(order);
+    } else if (one_launch) {
+      groups->push_back(order);   // the only level: [5, 10] + resampler, DC_SCAN
     } else if (six) {
       *front6 = true;
       groups->emplace_back(order.begin(), order.begin() + 6);
@@ -218,7 +231,7 @@ struct Frontend {
     if (plan.bits > 8) return fail(PMR446_EINVAL, "resampler filter bank larger than 256 rows");
     std::vector<std::vector<int>> groups;   // pre-launch groups, then the arb launch
     bool want_fused = false, want_front6 = false;
-    if (int rc = plan_groups(plan, in_fmt, &groups, &want_fused, &want_front6)) return rc;
+    if (int rc = plan_groups(plan, in_fmt, &groups, &want_fused, &want_front6, dc)) return rc;
     levels.resize(groups.size());
     long long max_in = max_chunk;
     int stage_cursor = (int)plan.stages - 1;  // index into plan.m / plan.hb of the next stage to place

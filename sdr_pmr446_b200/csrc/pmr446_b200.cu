@@ -753,7 +753,7 @@ extern "C" int pmr446_describe_frontend(float rate, float as, int in_fmt, int wi
   design::MsresampPlan p = design::msresamp_plan(rate, as);
   std::vector<std::vector<int>> groups;
   bool fused = false, front6 = false;
-  if (int rc = Frontend::plan_groups(p, in_fmt, &groups, &fused, &front6)) return rc;
+  if (int rc = Frontend::plan_groups(p, in_fmt, &groups, &fused, &front6, with_dc != 0)) return rc;
   std::string out;
   for (size_t l = 0; l < groups.size(); l++) {
     const bool arb = l + 1 == groups.size();
