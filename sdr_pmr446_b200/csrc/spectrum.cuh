@@ -20,6 +20,8 @@
 
 namespace pmr {
 
+template <int R>
+__device__ __forceinline__ void wf_stage(const float2* __restrict__ x, float2* __restrict__ y, const float2* __restrict__ tw, int N, int Ns);
 struct WfParams {
   const float2* res;       // resampler output ring
   long long res_stride, res_mask;
@@ -28,6 +30,7 @@ struct WfParams {
   int W, nfft, hop;
   int n_transforms;        // floor(ny / hop)
   int parts;               // blocks per stream
+  int groups, tg;          // block-per-transform kernel: independent thread groups per block and threads per group
   const float* window;     // [W] scaled Hann
   const float2* twiddle;   // [nfft] exp(-2 pi i k / nfft)
   int n_stages;
@@ -61,18 +64,24 @@ __device__ __forceinline__ void dft5(float2* v) {
 }
 
 template <int R>
-__device__ __forceinline__ void wf_stage(const float2* __restrict__ x, float2* __restrict__ y, const float2* __restrict__ tw, int N, int Ns) {
+__device__ __forceinline__ void wf_stage(const float2* __restrict__ x, float2* __restrict__ y, const float2* __restrict__ tw, int N, int Ns,
+                                         int first, int stride) {
   const int nb = N / R;
-  for (int j = threadIdx.x; j < nb; j += blockDim.x) {
-    const int k = j % Ns;
+  const int tstep = N / (Ns * R);
+  const float inv_ns = 1.0f / (float)Ns;
+  for (int j = first; j < nb; j += stride) {
+    const int k = j - (int)(((float)j + 0.5f) * inv_ns) * Ns;   // j mod Ns without an integer division (exact for j < 2^20)
     float2 v[R];
-    const int tstep = N / (Ns * R);
+    // twiddles W^(r k tstep), r = 1 .. R-1, as powers of ONE table entry: the gathers (a different cache line per lane in
+    // the early stages) made these stages load/store-bound
+    const float2 w1 = tw[k * tstep];
+    float2 wr = w1;
 #pragma unroll
     for (int r = 0; r < R; r++) {
       float2 a = x[j + r * nb];
       if (r > 0) {
-        const float2 w = tw[(r * k * tstep) % N];
-        a = make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+        a = make_float2(a.x * wr.x - a.y * wr.y, a.x * wr.y + a.y * wr.x);
+        if (r + 1 < R) wr = make_float2(wr.x * w1.x - wr.y * w1.y, wr.x * w1.y + wr.y * w1.x);
       }
       v[r] = a;
     }
@@ -95,6 +104,11 @@ __device__ __forceinline__ void wf_stage(const float2* __restrict__ x, float2* _
       for (int q = 0; q < R; q++) y[j0 + q * Ns] = v[q];
     }
   }
+}
+
+template <int R>
+__device__ __forceinline__ void wf_stage(const float2* __restrict__ x, float2* __restrict__ y, const float2* __restrict__ tw, int N, int Ns) {
+  wf_stage<R>(x, y, tw, N, Ns, (int)threadIdx.x, (int)blockDim.x);
 }
 
 // generic prime radix p (reads straight from shared memory, O(p) per output).  One work item per OUTPUT (j, q), so
@@ -121,22 +135,30 @@ __device__ __forceinline__ void wf_stage_generic(int R, const float2* __restrict
   }
 }
 
+// Large transforms (nfft > 1024, e.g. 6400 for the wideband configuration's W = 1600).  A block holds `groups` independent
+// thread groups of `tg` threads; each group walks its own transforms with its own ping-pong buffers and its own named barrier,
+// so while one group waits at a stage barrier the other one computes (one 1024-thread group per block -- round 1 -- spent
+// most of its time at those barriers).  |X|^2 accumulates in registers (bins lt + k tg).
+constexpr int WFB_NM = 16;   // accumulator registers per thread: nfft <= 16 tg
 static __global__ void __launch_bounds__(1024) wf_accumulate_kernel(WfParams p) {
   extern __shared__ float2 wf_smem[];
-  float2* a = wf_smem;
-  float2* b = wf_smem + p.nfft;
-  float* acc = (float*)(wf_smem + 2 * p.nfft);
+  const int g = threadIdx.x / p.tg, lt = threadIdx.x - g * p.tg;
+  float2* a = wf_smem + (size_t)g * 2 * p.nfft;
+  float2* b = a + p.nfft;
+  auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(p.tg) : "memory"); };
   const int s = blockIdx.x / p.parts, part = blockIdx.x % p.parts;
   const float2* res = p.res + (long long)s * p.res_stride;
-  for (int i = threadIdx.x; i < p.nfft; i += blockDim.x) acc[i] = 0.0f;
+  float acc[WFB_NM];
+#pragma unroll
+  for (int k = 0; k < WFB_NM; k++) acc[k] = 0.0f;
   // transform t (1-based) fires after t*hop samples of the chunk and sees the last W of them
-  for (int t = 1 + part; t <= p.n_transforms; t += p.parts) {
-    __syncthreads();
+  for (int t = 1 + part * p.groups + g; t <= p.n_transforms; t += p.parts * p.groups) {
+    group_sync();
     const long long first = (long long)t * p.hop - p.W;  // chunk-local index of window sample 0
     // nfft = 4 W with a leading radix-4 stage: its inputs 1..3 are the zero padding, so the stage is the load itself
     const bool lead4 = p.radix[0] == 4 && p.nfft == 4 * p.W;
     if (lead4) {
-      for (int i = threadIdx.x; i < p.W; i += blockDim.x) {
+      for (int i = lt; i < p.W; i += p.tg) {
         const long long li = first + i;
         float2 v = make_float2(0.0f, 0.0f);
         if (li >= 0) {
@@ -147,7 +169,7 @@ static __global__ void __launch_bounds__(1024) wf_accumulate_kernel(WfParams p) 
         b[4 * i] = v; b[4 * i + 1] = v; b[4 * i + 2] = v; b[4 * i + 3] = v;
       }
     } else {
-      for (int i = threadIdx.x; i < p.nfft; i += blockDim.x) {
+      for (int i = lt; i < p.nfft; i += p.tg) {
         float2 v = make_float2(0.0f, 0.0f);
         if (i < p.W) {
           const long long li = first + i;
@@ -160,25 +182,32 @@ static __global__ void __launch_bounds__(1024) wf_accumulate_kernel(WfParams p) 
         a[i] = v;
       }
     }
-    __syncthreads();
+    group_sync();
     float2 *x = lead4 ? b : a, *y = lead4 ? a : b;
     int Ns = lead4 ? 4 : 1;
     for (int st = lead4 ? 1 : 0; st < p.n_stages; st++) {
       const int R = p.radix[st];
-      if (R == 4) wf_stage<4>(x, y, p.twiddle, p.nfft, Ns);
-      else if (R == 2) wf_stage<2>(x, y, p.twiddle, p.nfft, Ns);
-      else if (R == 3) wf_stage<3>(x, y, p.twiddle, p.nfft, Ns);
-      else if (R == 5) wf_stage<5>(x, y, p.twiddle, p.nfft, Ns);
-      else wf_stage_generic(R, x, y, p.twiddle, p.nfft, Ns, threadIdx.x, blockDim.x);
+      if (R == 4) wf_stage<4>(x, y, p.twiddle, p.nfft, Ns, lt, p.tg);
+      else if (R == 2) wf_stage<2>(x, y, p.twiddle, p.nfft, Ns, lt, p.tg);
+      else if (R == 3) wf_stage<3>(x, y, p.twiddle, p.nfft, Ns, lt, p.tg);
+      else if (R == 5) wf_stage<5>(x, y, p.twiddle, p.nfft, Ns, lt, p.tg);
+      else wf_stage_generic(R, x, y, p.twiddle, p.nfft, Ns, lt, p.tg);
       Ns *= R;
       float2* tmp = x; x = y; y = tmp;
-      __syncthreads();
+      group_sync();
     }
-    for (int i = threadIdx.x; i < p.nfft; i += blockDim.x) acc[i] += x[i].x * x[i].x + x[i].y * x[i].y;
+#pragma unroll
+    for (int k = 0; k < WFB_NM; k++) {
+      const int i = lt + k * p.tg;
+      if (i < p.nfft) { const float2 z = x[i]; acc[k] = fmaf(z.x, z.x, fmaf(z.y, z.y, acc[k])); }
+    }
   }
-  __syncthreads();
-  float* out = p.partial + ((long long)s * p.parts + part) * p.nfft;
-  for (int i = threadIdx.x; i < p.nfft; i += blockDim.x) out[i] = acc[i];
+  float* out = p.partial + (((long long)s * p.parts + part) * p.groups + g) * p.nfft;
+#pragma unroll
+  for (int k = 0; k < WFB_NM; k++) {
+    const int i = lt + k * p.tg;
+    if (i < p.nfft) out[i] = acc[k];
+  }
 }
 
 // ---- small transforms (nfft <= 1024): one WARP per transform ----------------------------------------------------------
@@ -388,6 +417,7 @@ struct Waterfall {
   size_t smem = 0;
   bool warp_kernel = false;   // nfft <= 1024: one warp per transform
   int wf_warps = 1;
+  int groups = 1, tg = 256;   // block-per-transform kernel: thread groups per block, threads per group
   int fast_p = 0;             // W = 8 P with P in {8, 10, 12, 15, 16, 20}: register-resident kernel (spectrum_fast.cuh)
   float2 twp[WFF_MAXP];
 
@@ -423,20 +453,24 @@ struct Waterfall {
       }
     }
     warp_kernel = nfft <= 1024;
+    if (!warp_kernel && !fast_p) {
+      tg = nfft > 4096 ? 512 : 256;                                   // nfft <= 8192 = 16 tg
+      groups = (int)std::max<size_t>(1, std::min<size_t>(1024 / tg, (200 * 1024) / ((size_t)nfft * 2 * sizeof(float2))));
+    }
     wf_warps = std::max(1, std::min(WFW_WARPS, (int)((96 * 1024 / (nfft * sizeof(float2)) - 1) / 2)));
     {
-      const size_t per_block = warp_kernel ? (size_t)nfft * sizeof(float2) * (1 + 2 * wf_warps) : (size_t)nfft * (2 * sizeof(float2) + sizeof(float));
+      const size_t per_block = warp_kernel ? (size_t)nfft * sizeof(float2) * (1 + 2 * wf_warps) : (size_t)nfft * 2 * sizeof(float2) * groups;
       const int per_sm = fast_p ? 3 : (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / per_block));
       // the fast kernel's blocks are long (a whole stream's transforms): eight waves of them keep the tail short
       parts = std::max(1, std::min(128, ((fast_p ? 8 : 1) * 148 * per_sm + S - 1) / S));
     }
     int rc;
     if ((rc = d_window.alloc(W * sizeof(float))) || (rc = d_twiddle.alloc(nfft * sizeof(float2))) ||
-        (rc = d_partial.alloc((size_t)S * parts * nfft * sizeof(float))) || (rc = d_scratch.alloc((size_t)S * nfft * sizeof(float))))
+        (rc = d_partial.alloc((size_t)S * parts * groups * nfft * sizeof(float))) || (rc = d_scratch.alloc((size_t)S * nfft * sizeof(float))))
       return rc;
     CUDA_TRY(cudaMemcpy(d_window.p, w.data(), W * sizeof(float), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d_twiddle.p, tw.data(), nfft * sizeof(float2), cudaMemcpyHostToDevice));
-    smem = warp_kernel ? (size_t)nfft * sizeof(float2) * (1 + 2 * wf_warps) : (size_t)nfft * (2 * sizeof(float2) + sizeof(float));
+    smem = warp_kernel ? (size_t)nfft * sizeof(float2) * (1 + 2 * wf_warps) : (size_t)nfft * 2 * sizeof(float2) * groups;
     if (warp_kernel && smem > 48 * 1024) {
       CUDA_TRY(cudaFuncSetAttribute(wf_accumulate_warp_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       CUDA_TRY(cudaFuncSetAttribute(wf_accumulate_warp_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -460,6 +494,8 @@ struct Waterfall {
     p.hop = (int)(W / 2);
     p.n_transforms = (int)(ny / p.hop);
     p.parts = parts;
+    p.groups = groups;
+    p.tg = tg;
     p.window = (const float*)d_window.p;
     p.twiddle = (const float2*)d_twiddle.p;
     p.n_stages = (int)radix.size();
@@ -484,12 +520,12 @@ struct Waterfall {
       if (warp_kernel && nfft <= 256) wf_accumulate_warp_kernel<8><<<S * parts, 32 * wf_warps, smem, st>>>(p);
       else if (warp_kernel && nfft <= 512) wf_accumulate_warp_kernel<16><<<S * parts, 32 * wf_warps, smem, st>>>(p);
       else if (warp_kernel) wf_accumulate_warp_kernel<32><<<S * parts, 32 * wf_warps, smem, st>>>(p);
-      else wf_accumulate_kernel<<<S * parts, smem > 48 * 1024 ? 1024 : 256, smem, st>>>(p);
+      else wf_accumulate_kernel<<<S * parts, groups * tg, smem, st>>>(p);
       (*launches)++;
     }
     WfFinalParams f;
     f.partial = p.partial;
-    f.parts = parts;
+    f.parts = (warp_kernel || fast_p) ? parts : parts * groups;
     f.W = p.W;
     f.nfft = p.nfft;
     f.n_transforms = p.n_transforms;
