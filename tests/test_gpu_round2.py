@@ -222,3 +222,39 @@ def test_other_resampler_plans(fs, M, fmt_cu8):
         assert rel_rms(g["demod"][0, c, sl], r["demod"][c, sl]) < REL_RMS_TOL, ("demod", c)
         dp = np.abs(g["pcm"][0, c, 600:].astype(np.int32) - r["pcm"][c, 600:].astype(np.int32))
         assert dp.max() <= PCM_TOL_LSB, ("pcm", c, int(dp.max()))
+
+
+def test_deferred_dc_correction_path_float_parity():
+    """2.4 Msps cu8 WITHOUT the `res` output and without a waterfall: the fused front end leaves the zero-input part of its
+    DC blocker to channelize16_kernel (added while it stages its tiles; the ring's tail is then finished in place).  Channelizer
+    and discriminator outputs at 1e-4, s16 within 1 LSB, over chunk sizes that split tiles, batches and segments, including
+    chunks smaller than a tile, and the stream start (DC state zero) as well as a DC offset 10x the default."""
+    from oracle import oracle as orc
+    from sdr_pmr446_b200 import chain, synth
+    fs, n = 2400000, 900000
+    for dc in (0.02 - 0.015j, 0.2 - 0.15j):
+        car = synth.rotated_carriers(4)
+        spec = synth.CaptureSpec(fs=float(fs), carriers=car, dc=dc)
+        iq = synth.make_cu8(spec, n, 455)
+        gpu = chain.PmrBatch(n_streams=1, fs_in=fs, in_fmt=1, audio_gain=1.0, max_chunk=300000)
+        sizes = [300000, 1, 47, 6143, 6145, 73729, 200000, 13, 300000, 13922]
+        assert sum(sizes) == n
+        parts, o = [], 0
+        for k in sizes:
+            parts.append(gpu.execute(iq[None, 2 * o:2 * (o + k)], want=("chan", "demod", "pcm")))
+            o += k
+        gpu.close()
+        g = {"ns": sum(p["ns"] for p in parts)}
+        for k in ("chan", "demod", "pcm"):
+            g[k] = np.concatenate([p[k] for p in parts], axis=-1)
+        ref = orc.PmrOracle(fs_in=fs, in_fmt=1, audio_gain=1.0, chunk=300000)
+        r = ref.run(iq, 300000, want=("chan", "demod", "pcm"))
+        ref.close()
+        assert g["ns"] == r["ns"]
+        assert rel_rms(g["chan"][0], r["chan"]) < REL_RMS_TOL
+        for c in active_channels(car):
+            assert rel_rms(g["chan"][0, c], r["chan"][c]) < REL_RMS_TOL, ("chan", c)
+            sl = slice(1, None) if g["demod"][0, c, 0] == r["demod"][c, 0] else slice(500, None)
+            assert rel_rms(g["demod"][0, c, sl], r["demod"][c, sl]) < REL_RMS_TOL, ("demod", c)
+            dp = np.abs(g["pcm"][0, c, 600:].astype(np.int32) - r["pcm"][c, 600:].astype(np.int32))
+            assert dp.max() <= PCM_TOL_LSB, ("pcm", c, int(dp.max()))
