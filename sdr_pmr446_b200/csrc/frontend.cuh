@@ -425,6 +425,56 @@ static __global__ void __launch_bounds__(128) dc_scan_kernel(DcScanParams p) {
   if (lane == 0) p.v_lag[s] = carry;
 }
 
+// The same scan with one BLOCK of 256 threads per stream (256 segments per pass): for a few streams with thousands of
+// segments each (the wideband configuration: 4 streams x 7800 segments) the warp version above is a long serial loop.
+static __global__ void __launch_bounds__(256) dc_scan_block_kernel(DcScanParams p) {
+  __shared__ float wd[8], wsx[8], wsy[8];
+  __shared__ float2 s_carry;
+  const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = p.v_lag[s];
+  __syncthreads();
+  for (int base = 0; base < p.nseg; base += 256) {
+    const float2 carry = s_carry;
+    const int t = base + threadIdx.x;
+    float d = 1.0f;
+    float2 sm = make_float2(0.0f, 0.0f);
+    if (t < p.nseg) {
+      long long a = p.p0 + (long long)t * p.seg_len, b = a + p.seg_len;
+      if (b > p.end) b = p.end;
+      if (a < 0) a = 0;
+      const long long len = b - a;
+      if (len > 0) {
+        d = (len == p.seg_len) ? p.decay_full : powf(p.c, (float)len);
+        sm = p.sums[(long long)s * p.nseg + t];
+      }
+    }
+    // inclusive scan of the affine maps V -> d V + s inside the warp: (d2, s2) o (d1, s1) = (d1 d2, d2 s1 + s2)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float dp = __shfl_up_sync(0xffffffffu, d, o);
+      const float sx = __shfl_up_sync(0xffffffffu, sm.x, o), sy = __shfl_up_sync(0xffffffffu, sm.y, o);
+      if (lane >= o) {
+        sm.x = fmaf(d, sx, sm.x);
+        sm.y = fmaf(d, sy, sm.y);
+        d *= dp;
+      }
+    }
+    if (lane == 31) { wd[warp] = d; wsx[warp] = sm.x; wsy[warp] = sm.y; }
+    __syncthreads();
+    // the maps of the preceding warps, composed in order, applied to the carry: V before this warp's first segment
+    float2 vin = carry;
+    for (int w = 0; w < warp; w++) vin = make_float2(fmaf(wd[w], vin.x, wsx[w]), fmaf(wd[w], vin.y, wsy[w]));
+    const float2 after = make_float2(fmaf(d, vin.x, sm.x), fmaf(d, vin.y, sm.y));
+    float bx = __shfl_up_sync(0xffffffffu, after.x, 1), by = __shfl_up_sync(0xffffffffu, after.y, 1);
+    if (lane == 0) { bx = vin.x; by = vin.y; }
+    if (t < p.nseg) p.v_seg[(long long)s * p.nseg + t] = make_float2(bx, by);
+    __syncthreads();
+    if (threadIdx.x == 255) s_carry = after;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) p.v_lag[s] = s_carry;
+}
+
 // in-place zero-input-response correction of the last `count` samples of a ring (they are the
 // next chunk's history, which the next launch reads as already corrected)
 static __global__ void zir_tail_kernel(float2* ring, long long ring_stride, long long ring_mask, Correction c, long long start, int count) {

@@ -374,6 +374,12 @@ struct Frontend {
 
   // Consumes n raw samples per stream ([n_in, n_in + n)); afterwards n_out is the absolute
   // number of output samples in the `out` ring.
+  // few streams with many segments: one block per stream; otherwise one warp per stream
+  void launch_dc_scan(const DcScanParams& sp, cudaStream_t st) const {
+    if (S <= 64 && sp.nseg > 128) dc_scan_block_kernel<<<S, 256, 0, st>>>(sp);
+    else dc_scan_kernel<<<(unsigned)(((long long)S * 32 + 127) / 128), 128, 0, st>>>(sp);
+  }
+
   // defer_zir: the caller's consumer applies pending_corr() while it reads the ring and then calls fix_pending(false);
   // otherwise execute() finishes the ring itself (one extra read-modify-write pass over the new samples).
   const Correction* pending_corr() const { return has_pending ? &pending : nullptr; }
@@ -456,7 +462,7 @@ struct Frontend {
         dp.sums = (float2*)sums.p;
         if (L.src == SRC_CU8) dc_local_kernel<SRC_CU8><<<blocks, 128, 0, st>>>(dp);
         else dc_local_kernel<SRC_CF32><<<blocks, 128, 0, st>>>(dp);
-        dc_scan_kernel<<<(unsigned)(((long long)S * 32 + 127) / 128), 128, 0, st>>>(sp);
+        launch_dc_scan(sp, st);
         *launches += 2;
         tm->mark(st, TM_DC);
       }
@@ -588,7 +594,7 @@ struct Frontend {
         if (out1 > out0) new_out = L.arb ? (long long)design::arb_outputs_after((uint64_t)out1, plan.step) : out1;
       }
       if (L.dc == DC_ZSR && nseg > 0) {   // chain the local sums the cascade just wrote into V0 per segment
-        dc_scan_kernel<<<(unsigned)(((long long)S * 32 + 127) / 128), 128, 0, st>>>(sp);
+        launch_dc_scan(sp, st);
         *launches += 1;
         tm->mark(st, TM_DC);
         // ring samples per input sample of this level: 1 / D, or 1 / 12 with the x 2/3 resampler fused in
