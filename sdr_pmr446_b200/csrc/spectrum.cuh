@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "common_host.hpp"
+#include "reg_dft.cuh"
 
 namespace pmr {
 
@@ -37,31 +38,6 @@ struct WfParams {
   int radix[16];
   float* partial;          // [n_streams][parts][nfft]
 };
-
-// forward DFTs of 3 and 5 points with constant coefficients (in place: v[q] <- sum_r v[r] W_R^(q r))
-__device__ __forceinline__ void dft3(float2* v) {
-  const float s = 0.86602540378443865f;
-  const float2 t1 = make_float2(v[1].x + v[2].x, v[1].y + v[2].y);
-  const float2 t2 = make_float2(fmaf(-0.5f, t1.x, v[0].x), fmaf(-0.5f, t1.y, v[0].y));
-  const float2 t3 = make_float2(s * (v[1].x - v[2].x), s * (v[1].y - v[2].y));
-  v[0] = make_float2(v[0].x + t1.x, v[0].y + t1.y);
-  v[1] = make_float2(t2.x + t3.y, t2.y - t3.x);   // t2 - i t3
-  v[2] = make_float2(t2.x - t3.y, t2.y + t3.x);   // t2 + i t3
-}
-__device__ __forceinline__ void dft5(float2* v) {
-  const float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f, s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;
-  const float2 a1 = make_float2(v[1].x + v[4].x, v[1].y + v[4].y), a2 = make_float2(v[2].x + v[3].x, v[2].y + v[3].y);
-  const float2 b1 = make_float2(v[1].x - v[4].x, v[1].y - v[4].y), b2 = make_float2(v[2].x - v[3].x, v[2].y - v[3].y);
-  const float2 p1 = make_float2(fmaf(c2, a2.x, fmaf(c1, a1.x, v[0].x)), fmaf(c2, a2.y, fmaf(c1, a1.y, v[0].y)));
-  const float2 p2 = make_float2(fmaf(c1, a2.x, fmaf(c2, a1.x, v[0].x)), fmaf(c1, a2.y, fmaf(c2, a1.y, v[0].y)));
-  const float2 q1 = make_float2(fmaf(s2, b2.x, s1 * b1.x), fmaf(s2, b2.y, s1 * b1.y));
-  const float2 q2 = make_float2(fmaf(-s1, b2.x, s2 * b1.x), fmaf(-s1, b2.y, s2 * b1.y));
-  v[0] = make_float2(v[0].x + a1.x + a2.x, v[0].y + a1.y + a2.y);
-  v[1] = make_float2(p1.x + q1.y, p1.y - q1.x);   // p1 - i q1
-  v[4] = make_float2(p1.x - q1.y, p1.y + q1.x);   // p1 + i q1
-  v[2] = make_float2(p2.x + q2.y, p2.y - q2.x);   // p2 - i q2
-  v[3] = make_float2(p2.x - q2.y, p2.y + q2.x);   // p2 + i q2
-}
 
 template <int R>
 __device__ __forceinline__ void wf_stage(const float2* __restrict__ x, float2* __restrict__ y, const float2* __restrict__ tw, int N, int Ns,
