@@ -374,6 +374,9 @@ __global__ void __launch_bounds__(128) dc_local_kernel(DcLocalParams p) {
 }
 
 struct DcScanParams {
+  // The fused cu8 front end runs its recurrence on X = u8 - 127 (exact integers) instead of x = X / 128 + c0' (see
+  // cu8_pair_x): sums / v_lag are then in X units and the consumers' V0 is unit_scale * V_X.  Every other plan: 1.
+  float unit_scale;
   int n_streams, nseg;
   const float2* sums;
   float2* v_seg;      // out: V at each segment's warm-up start
@@ -418,7 +421,7 @@ static __global__ void __launch_bounds__(128) dc_scan_kernel(DcScanParams p) {
     float2 after = make_float2(fmaf(d, carry.x, sm.x), fmaf(d, carry.y, sm.y));
     float bx = __shfl_up_sync(0xffffffffu, after.x, 1), by = __shfl_up_sync(0xffffffffu, after.y, 1);
     if (lane == 0) { bx = carry.x; by = carry.y; }
-    if (t < p.nseg) p.v_seg[(long long)s * p.nseg + t] = make_float2(bx, by);
+    if (t < p.nseg) p.v_seg[(long long)s * p.nseg + t] = make_float2(p.unit_scale * bx, p.unit_scale * by);
     carry.x = __shfl_sync(0xffffffffu, after.x, 31);
     carry.y = __shfl_sync(0xffffffffu, after.y, 31);
   }
@@ -467,7 +470,7 @@ static __global__ void __launch_bounds__(256) dc_scan_block_kernel(DcScanParams 
     const float2 after = make_float2(fmaf(d, vin.x, sm.x), fmaf(d, vin.y, sm.y));
     float bx = __shfl_up_sync(0xffffffffu, after.x, 1), by = __shfl_up_sync(0xffffffffu, after.y, 1);
     if (lane == 0) { bx = vin.x; by = vin.y; }
-    if (t < p.nseg) p.v_seg[(long long)s * p.nseg + t] = make_float2(bx, by);
+    if (t < p.nseg) p.v_seg[(long long)s * p.nseg + t] = make_float2(p.unit_scale * bx, p.unit_scale * by);
     __syncthreads();
     if (threadIdx.x == 255) s_carry = after;
     __syncthreads();

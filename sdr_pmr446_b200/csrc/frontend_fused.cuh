@@ -32,6 +32,7 @@ constexpr int FF_SLOTS = 29 + 13;   // shared-memory history per thread: m = 10 
 struct FusedParams {
   CascadeParams c;       // source view, segment grid, DC blocker, destination ring, hb[0..2] = taps of m = 3, 5, 10
   float arb[2][14];      // filter-bank rows of the two resampler phases, newest first
+  float w0;              // DC blocker state (X units) of a stream that has been silent for ever: CU8_XBIAS / alpha
 };
 
 // one half-band decimator stage on pairs: out[o] = x_odd[o - M] + sum_{j < 2M} h[j] x_even[o - j]   (A.4)
@@ -83,6 +84,21 @@ __device__ __forceinline__ float2 cu8_pair(unsigned w, int k) {
                                  __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + (unsigned)(2 * k + 1))));
   const float2 u = fadd2(raw, make_float2(-8388608.0f, -8388608.0f));
   return ffma2(u, make_float2(1.0f / 128.0f, 1.0f / 128.0f), make_float2(-127.4f / 128.0f, -127.4f / 128.0f));
+}
+
+// cu8 -> X = u8 - 127 as an exact small integer (one PRMT per byte + one packed FADD2 per sample).  The sample itself is
+// x = X / 128 + c0' with c0' = -(fl(127.4) - 127) / 128, both exactly representable, and everything after it is linear:
+// the 1 / 128 rides on the kernel's final power-of-two scale (exact), and the constant c0' is what the DC blocker removes
+// -- in X units "x was zero for ever" is the blocker state W = CU8_XBIAS / alpha instead of 0, which is where the segment
+// that starts at the head of a stream starts (FusedParams::w0); every other segment starts from zero state as before and
+// the affine scan carries the difference.  With V_X(0) = w0 the true state is exactly v = V_X / 128 + c0' / alpha, so the
+// zero-input term the consumers add is -alpha (V_X / 128) E[k]: DcScanParams::unit_scale, nothing else changes.
+// One FMA-pipe instruction per sample less than cu8_pair (7.5 % of the fused kernel's FMA work).
+constexpr float CU8_XBIAS = 127.40000152587890625f - 127.0f;   // X of a zero-valued ("no sample") x
+__device__ __forceinline__ float2 cu8_pair_x(unsigned w, int k) {
+  const float2 raw = make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + (unsigned)(2 * k))),
+                                 __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + (unsigned)(2 * k + 1))));
+  return fadd2(raw, make_float2(-8388735.0f, -8388735.0f));    // -(2^23 + 127)
 }
 
 // The same conversion as a table look-up: 256 entries, each replicated for the 32 lanes at a 256-byte pitch, so ONE PRMT
@@ -162,6 +178,7 @@ __global__ void __launch_bounds__(FF_THREADS, NB) fused_frontend_kernel(FusedPar
 #pragma unroll
   for (int i = 0; i < 13; i++) aw[i] = make_float2(0.0f, 0.0f);
   float2 v = make_float2(0.0f, 0.0f);                              // DC blocker state (zero-state response)
+  if ((DC == DC_ZSR) && !LUT && T0 - p.halo <= 0) v = make_float2(fp.w0, fp.w0);   // head of the stream: see cu8_pair_x
 
   float2* dst = p.dst + (long long)s * p.dst_stride;
   const unsigned dmask = (unsigned)p.dst_mask;
@@ -171,6 +188,7 @@ __global__ void __launch_bounds__(FF_THREADS, NB) fused_frontend_kernel(FusedPar
 
   Loader<SRC_CU8> ld;
   ld.template init<FF_SUB>(p.src, s, qb);
+  constexpr bool XU = (DC == DC_ZSR) && !LUT;   // integer-unit recurrence (cu8_pair_x); the host folds 1 / 128 into p.scale
   const int n_sub = 3 * n_it;
   Raw<SRC_CU8, FF_SUB> raw[3];
   // Loads go through L1 here (unlike cascade_kernel's no-allocate loads): with ~250 registers per thread ptxas sinks the
@@ -203,14 +221,15 @@ __global__ void __launch_bounds__(FF_THREADS, NB) fused_frontend_kernel(FusedPar
       if (FAST) {
 #pragma unroll
         for (int j = 0; j < FF_SUB / 2; j++) {
-          x[2 * j] = LUT ? cu8_pair_lut(ff_lut, lane4, raw[sub].w[j], 0) : cu8_pair(raw[sub].w[j], 0);
-          x[2 * j + 1] = LUT ? cu8_pair_lut(ff_lut, lane4, raw[sub].w[j], 1) : cu8_pair(raw[sub].w[j], 1);
+          x[2 * j] = LUT ? cu8_pair_lut(ff_lut, lane4, raw[sub].w[j], 0) : (XU ? cu8_pair_x(raw[sub].w[j], 0) : cu8_pair(raw[sub].w[j], 0));
+          x[2 * j + 1] = LUT ? cu8_pair_lut(ff_lut, lane4, raw[sub].w[j], 1) : (XU ? cu8_pair_x(raw[sub].w[j], 1) : cu8_pair(raw[sub].w[j], 1));
         }
       } else {
         float xr[FF_SUB], xi[FF_SUB];
         ld.template convert<FF_SUB>(p.src, qb + (long long)sbi * FF_SUB, sbi, raw[sub], xr, xi);
 #pragma unroll
-        for (int i = 0; i < FF_SUB; i++) x[i] = make_float2(xr[i], xi[i]);
+        for (int i = 0; i < FF_SUB; i++)   // X = (x - c0') * 128, exact (a sample) or CU8_XBIAS (a zero: before the stream start)
+          x[i] = XU ? make_float2(fmaf(xr[i], 128.0f, CU8_XBIAS), fmaf(xi[i], 128.0f, CU8_XBIAS)) : make_float2(xr[i], xi[i]);
       }
       if (DC != DC_NONE) {
         // A.1 dc blocker, zero-state part: y = x - alpha v[n-1], v[n] = (1 - alpha) v[n-1] + x.  Only the one-FFMA2

@@ -374,6 +374,10 @@ struct Frontend {
 
   // Consumes n raw samples per stream ([n_in, n_in + n)); afterwards n_out is the absolute
   // number of output samples in the `out` ring.
+  static bool fused_lut() {   // tuning probe: table look-up conversion (x units) instead of the integer-unit recurrence
+    static const bool on = getenv("PMR446_FF_CVT") && strcmp(getenv("PMR446_FF_CVT"), "lut") == 0;
+    return on;
+  }
   // few streams with many segments: one block per stream; otherwise one warp per stream
   void launch_dc_scan(const DcScanParams& sp, cudaStream_t st) const {
     if (S <= 64 && sp.nseg > 128) dc_scan_block_kernel<<<S, 256, 0, st>>>(sp);
@@ -449,6 +453,7 @@ struct Frontend {
         sp.end = seg0_next - L.halo;
         sp.c = c_pole;
         sp.decay_full = (float)pow((double)c_pole, (double)L.seg_len);
+        sp.unit_scale = (L.fused && L.dc == DC_ZSR && !fused_lut()) ? 1.0f / 128.0f : 1.0f;   // cu8_pair_x
       }
       if (L.dc == DC_SCAN && nseg > 0) {   // V0 per segment up front: local sums, then the scan
         DcLocalParams dp;
@@ -538,7 +543,7 @@ struct Frontend {
           cp.halo = L.halo;
           cp.out0 = out0;
           cp.out1 = out1;
-          cp.scale = L.scale;
+          cp.scale = (L.dc == DC_ZSR && !fused_lut()) ? L.scale / 128.0f : L.scale;   // integer-unit recurrence: 2^-3 * 2^-7, exact
           cp.alpha = alpha_eff;
           cp.sums = (float2*)sums.p;
           cp.dc_end = seg0_next - L.halo;
@@ -547,9 +552,10 @@ struct Frontend {
           cp.dst_mask = L.cap - 1;
           memcpy(cp.hb, L.hb, sizeof cp.hb);
           memcpy(fp.arb, L.arb_rows, sizeof fp.arb);
+          fp.w0 = (float)((double)CU8_XBIAS / (double)alpha_eff);
           static const bool smem3 = getenv("PMR446_FF_VARIANT") && strcmp(getenv("PMR446_FF_VARIANT"), "smem3") == 0;   // tuning probe
           static const bool lut_cvt = [] {
-            const bool on = getenv("PMR446_FF_CVT") && strcmp(getenv("PMR446_FF_CVT"), "lut") == 0;
+            const bool on = fused_lut();
             if (on) cudaFuncSetAttribute(fused_frontend_kernel<DC_ZSR, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_LUT_BYTES);
             return on;
           }();
