@@ -303,6 +303,7 @@ __global__ void __launch_bounds__(FF_THREADS, NB) fused_frontend_kernel(FusedPar
 struct Front6Params {
   CascadeParams c;      // c.hb[0..3] = taps of stages 1-4 (all m = 3)
   float hb5[20], hb6[20];
+  float w0;             // as FusedParams::w0
 };
 constexpr int F6_G = 64, F6_D = 64;
 
@@ -338,6 +339,8 @@ __global__ void __launch_bounds__(FF_THREADS, 2) front6_kernel(Front6Params fp) 
   HbPair<MF, 1> sf;
   sa.reset(); sb.reset(); se.reset(); sf.reset();
   float2 v = make_float2(0.0f, 0.0f);
+  constexpr bool XU = (DC == DC_ZSR);   // integer-unit recurrence, see cu8_pair_x
+  if (XU && T0 - p.halo <= 0) v = make_float2(fp.w0, fp.w0);
   float2* dst = p.dst + (long long)s * p.dst_stride;
   const unsigned dmask = (unsigned)p.dst_mask, ob32 = (unsigned)ob;
   const float scale = p.scale;
@@ -376,12 +379,16 @@ __global__ void __launch_bounds__(FF_THREADS, 2) front6_kernel(Front6Params fp) 
         float2 x[FF_SUB];
         if (FAST) {
 #pragma unroll
-          for (int j = 0; j < FF_SUB / 2; j++) { x[2 * j] = cu8_pair(raw[sub].w[j], 0); x[2 * j + 1] = cu8_pair(raw[sub].w[j], 1); }
+          for (int j = 0; j < FF_SUB / 2; j++) {
+            x[2 * j] = XU ? cu8_pair_x(raw[sub].w[j], 0) : cu8_pair(raw[sub].w[j], 0);
+            x[2 * j + 1] = XU ? cu8_pair_x(raw[sub].w[j], 1) : cu8_pair(raw[sub].w[j], 1);
+          }
         } else {
           float xr[FF_SUB], xi[FF_SUB];
           ld.template convert<FF_SUB>(p.src, qb + (long long)sbi * FF_SUB, sbi, raw[sub], xr, xi);
 #pragma unroll
-          for (int i = 0; i < FF_SUB; i++) x[i] = make_float2(xr[i], xi[i]);
+          for (int i = 0; i < FF_SUB; i++)
+            x[i] = XU ? make_float2(fmaf(xr[i], 128.0f, CU8_XBIAS), fmaf(xi[i], 128.0f, CU8_XBIAS)) : make_float2(xr[i], xi[i]);
         }
         if (DC != DC_NONE) {
 #pragma unroll
