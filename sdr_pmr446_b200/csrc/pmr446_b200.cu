@@ -16,6 +16,7 @@
 #include "../../include/pmr446_b200.h"
 #include "../../include/pmr446_taps.h"
 #include "audio_fft.cuh"
+#include "audio_fft4.cuh"
 #include "backend.cuh"
 #include "channelizer.cuh"
 #include "channelizer_generic.cuh"
@@ -483,9 +484,23 @@ extern "C" int pmr446_batch_execute_device(pmr446_batch* b, const void* iq, long
       fp.audio = out->audio;
       fp.pcm = out->pcm;
       fp.out_ld = out->ld;
-      const unsigned fgrid = (unsigned)((long long)((fp.rows + 1) / 2) * fp.tiles);
-      if (b->fft_halo == AF_HALO) audio_fft_kernel<AF_HALO><<<fgrid, AF_T, 0, st>>>(fp);
-      else audio_fft_kernel<AF_HALO_LONG><<<fgrid, AF_T, 0, st>>>(fp);
+      // four rows per block, all-packed arithmetic (audio_fft4.cuh); PMR446_AUDIO_FFT=2 keeps round 1's two-row kernel (tuning probe)
+      static const bool four = [] {
+        const char* e = getenv("PMR446_AUDIO_FFT");
+        if (e && strcmp(e, "2") == 0) return false;
+        cudaFuncSetAttribute(audio_fft4_kernel<AF_HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, AF4_SMEM_BYTES);
+        cudaFuncSetAttribute(audio_fft4_kernel<AF_HALO_LONG>, cudaFuncAttributeMaxDynamicSharedMemorySize, AF4_SMEM_BYTES);
+        return true;
+      }();
+      if (four) {
+        const unsigned fgrid = (unsigned)((long long)((fp.rows + 3) / 4) * fp.tiles);
+        if (b->fft_halo == AF_HALO) audio_fft4_kernel<AF_HALO><<<fgrid, AF_T, AF4_SMEM_BYTES, st>>>(fp);
+        else audio_fft4_kernel<AF_HALO_LONG><<<fgrid, AF_T, AF4_SMEM_BYTES, st>>>(fp);
+      } else {
+        const unsigned fgrid = (unsigned)((long long)((fp.rows + 1) / 2) * fp.tiles);
+        if (b->fft_halo == AF_HALO) audio_fft_kernel<AF_HALO><<<fgrid, AF_T, 0, st>>>(fp);
+        else audio_fft_kernel<AF_HALO_LONG><<<fgrid, AF_T, 0, st>>>(fp);
+      }
       b->launches++;
       b->timer.mark(st, TM_AUDIO);
     }
