@@ -9,6 +9,14 @@
 // identical operations with identical twiddles, so a complex multiplication is four packed instructions for two products
 // (twiddle components as scalar-broadcast operands), a rotation by +-i is a pair swap that costs nothing, and the index /
 // predicate / barrier overhead of a tile is shared by four rows.
+//
+// Two more differences.  (1) The exchange buffer gives every k2 row 272 elements in BOTH layouts, so the rows a 16-thread group
+// (k2 = t >> 4) reads and writes in the middle passes are its own: five of the seven block barriers are __syncwarp() and the
+// eight warps of a block drift apart through the FP-heavy and the shared-memory-heavy phases instead of marching in step
+// (the FMA pipe was 56 % busy with 1.3 warps waiting on it per issue: phases, not capacity).  (2) Tiles are counted from the
+// call's first sample f0, not from the stream start: tile k yields outputs [f0 + k own, f0 + (k + 1) own), so a call of ns
+// samples costs ceil(ns / own) transforms.  Chunking therefore changes the summation order of the fast convolution (1e-7 of
+// the signal), like it changes the DC blocker's segment grid.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -104,10 +112,10 @@ static __global__ void __launch_bounds__(AF_T, 2) audio_fft4_kernel(AudioFftPara
   float2* const smi = af4_sm + AF_SMEM;
   const int t = threadIdx.x;
   const int quad = blockIdx.x / p.tiles;
-  const long long tile = p.tile0 + blockIdx.x % p.tiles;
+  const long long tile = blockIdx.x % p.tiles;                // counted from the call's first sample (anchored tiles)
   const int row0 = 4 * quad;
   const int nrow = p.rows - row0 < 4 ? p.rows - row0 : 4;   // rows that exist; the others compute on row0's samples, unused
-  const long long o0 = tile * AF_OWN - HALO;                // absolute index of tile sample 0
+  const long long o0 = p.f0 + tile * AF_OWN - HALO;         // absolute index of tile sample 0
   const float* d0 = p.demod + (long long)row0 * p.demod_stride;
   const float* d1 = p.demod + (long long)(nrow > 1 ? row0 + 1 : row0) * p.demod_stride;
   const float* d2 = p.demod + (long long)(nrow > 2 ? row0 + 2 : row0) * p.demod_stride;
@@ -144,17 +152,17 @@ static __global__ void __launch_bounds__(AF_T, 2) audio_fft4_kernel(AudioFftPara
   dft16_c2<false>(x);
   twiddle_powers_c2<false>(x, __ldg(p.tw + t));
 #pragma unroll
-  for (int k2 = 0; k2 < 16; k2++) { smr[k2 * 256 + t] = x[af_dig(k2)].r; smi[k2 * 256 + t] = x[af_dig(k2)].i; }
+  for (int k2 = 0; k2 < 16; k2++) { smr[k2 * 272 + t] = x[af_dig(k2)].r; smi[k2 * 272 + t] = x[af_dig(k2)].i; }
   __syncthreads();
   // thread (k2 = hi4, a = lo4): over b (-> k1), twiddle W^(16 a k1)
 #pragma unroll
-  for (int m = 0; m < 16; m++) { x[m].r = smr[hi4 * 256 + lo4 + 16 * m]; x[m].i = smi[hi4 * 256 + lo4 + 16 * m]; }
+  for (int m = 0; m < 16; m++) { x[m].r = smr[hi4 * 272 + lo4 + 16 * m]; x[m].i = smi[hi4 * 272 + lo4 + 16 * m]; }
   dft16_c2<false>(x);
   twiddle_powers_c2<false>(x, __ldg(p.tw + 16 * lo4));
-  __syncthreads();
+  __syncwarp();   // the exchange stays inside the 16-thread group (k2 = hi4), whose buffer rows no other warp touches here
 #pragma unroll
   for (int k1 = 0; k1 < 16; k1++) { smr[hi4 * 272 + k1 * 17 + lo4] = x[af_dig(k1)].r; smi[hi4 * 272 + k1 * 17 + lo4] = x[af_dig(k1)].i; }
-  __syncthreads();
+  __syncwarp();   // the exchange stays inside the 16-thread group (k2 = hi4), whose buffer rows no other warp touches here
   // thread (k2 = hi4, k1 = lo4): over a (-> k0)
 #pragma unroll
   for (int a = 0; a < 16; a++) { x[a].r = smr[hi4 * 272 + lo4 * 17 + a]; x[a].i = smi[hi4 * 272 + lo4 * 17 + a]; }
@@ -175,28 +183,27 @@ static __global__ void __launch_bounds__(AF_T, 2) audio_fft4_kernel(AudioFftPara
   // ---- inverse: over k0 (-> a), twiddle conj W^(a (16 k1 + k2)) ----
   dft16_c2<true>(x);
   twiddle_powers_c2<true>(x, __ldg(p.tw + 16 * lo4 + hi4));
-  __syncthreads();
+  __syncwarp();   // the exchange stays inside the 16-thread group (k2 = hi4), whose buffer rows no other warp touches here
 #pragma unroll
   for (int a = 0; a < 16; a++) { smr[hi4 * 272 + lo4 * 17 + a] = x[af_dig(a)].r; smi[hi4 * 272 + lo4 * 17 + a] = x[af_dig(a)].i; }
-  __syncthreads();
+  __syncwarp();   // the exchange stays inside the 16-thread group (k2 = hi4), whose buffer rows no other warp touches here
   // thread (k2 = hi4, a = lo4): over k1 (-> b), twiddle conj W^(16 b k2)
 #pragma unroll
   for (int k1 = 0; k1 < 16; k1++) { x[k1].r = smr[hi4 * 272 + k1 * 17 + lo4]; x[k1].i = smi[hi4 * 272 + k1 * 17 + lo4]; }
   dft16_c2<true>(x);
   twiddle_powers_c2<true>(x, __ldg(p.tw + 16 * hi4));
-  __syncthreads();
+  __syncwarp();   // the exchange stays inside the 16-thread group (k2 = hi4), whose buffer rows no other warp touches here
 #pragma unroll
-  for (int b = 0; b < 16; b++) { smr[hi4 * 256 + lo4 + 16 * b] = x[af_dig(b)].r; smi[hi4 * 256 + lo4 + 16 * b] = x[af_dig(b)].i; }
+  for (int b = 0; b < 16; b++) { smr[hi4 * 272 + lo4 + 16 * b] = x[af_dig(b)].r; smi[hi4 * 272 + lo4 + 16 * b] = x[af_dig(b)].i; }
   __syncthreads();
   // thread t: over k2 (-> m): tile samples t + 256 m
 #pragma unroll
-  for (int k2 = 0; k2 < 16; k2++) { x[k2].r = smr[k2 * 256 + t]; x[k2].i = smi[k2 * 256 + t]; }
+  for (int k2 = 0; k2 < 16; k2++) { x[k2].r = smr[k2 * 272 + t]; x[k2].i = smi[k2 * 272 + t]; }
   dft16_c2<true>(x);
 
   // ---- keep samples HALO.. of the tile that this call owns ----
-  const long long own_lo = (tile * AF_OWN > p.f0 ? tile * AF_OWN : p.f0) - o0;
-  const long long own_hi = ((tile + 1) * AF_OWN < p.f1 ? (tile + 1) * AF_OWN : p.f1) - o0;
-  const int s_lo = (int)(own_lo < HALO ? HALO : own_lo), s_hi = (int)(own_hi > AF_N ? AF_N : (own_hi < 0 ? 0 : own_hi));
+  const long long own_hi = (p.f0 + (tile + 1) * AF_OWN < p.f1 ? p.f0 + (tile + 1) * AF_OWN : p.f1) - o0;
+  const int s_lo = HALO, s_hi = (int)(own_hi > AF_N ? AF_N : (own_hi < 0 ? 0 : own_hi));
   const long long col0 = o0 - p.f0;   // column of tile sample 0
   const long long r0o = (long long)row0 * p.out_ld;
 #pragma unroll

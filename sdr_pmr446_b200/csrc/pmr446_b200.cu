@@ -493,6 +493,10 @@ extern "C" int pmr446_batch_execute_device(pmr446_batch* b, const void* iq, long
         return true;
       }();
       if (four) {
+        // tiles anchored at the call's first sample: ceil(ns / own) transforms per row instead of one more whenever the call
+        // straddles the absolute grid (3.49 tiles' worth of a 1 s step: 4 instead of 4.49 on average)
+        fp.tile0 = 0;
+        fp.tiles = (int)((f1 - f0 + af_own - 1) / af_own);
         const unsigned fgrid = (unsigned)((long long)((fp.rows + 3) / 4) * fp.tiles);
         if (b->fft_halo == AF_HALO) audio_fft4_kernel<AF_HALO><<<fgrid, AF_T, AF4_SMEM_BYTES, st>>>(fp);
         else audio_fft4_kernel<AF_HALO_LONG><<<fgrid, AF_T, AF4_SMEM_BYTES, st>>>(fp);
