@@ -21,8 +21,9 @@ struct dsd446_batch {
   int S = 0, device = 0;
   Frontend fe;                    // DC + decimating msresamp -> 12.5 kHz ring
   design::MsresampPlan up;        // interpolating msresamp_rrrf plan
-  DevBuf d_fm, d_z, d_pfb_up;
-  long long fm_cap = 0, z_cap = 0;
+  DevBuf d_fm, d_pfb_up;
+  long long fm_cap = 0;
+  int arb_period = 32;       // (near-)period of the up-sampler's phase sequence in outputs (dsd_backend_kernel)
   long long n_z = 0;              // arbitrary-resampler outputs produced so far
   long long max_res = 0, max_out = 0;
   DevBuf d_in, d_res, d_fmout, d_audio, d_pcm;
@@ -69,15 +70,27 @@ extern "C" int dsd446_batch_create(const dsd446_config* cfg, dsd446_batch** out)
     dsd446_batch_destroy(b);
     return fail(PMR446_EINVAL, "up-sampler plan not built: need one half-band stage after the arbitrary resampler (2 < rate <= 4)");
   }
+  if (b->up.step < (1u << 23) || b->up.step > (1u << 24)) {
+    dsd446_batch_destroy(b);
+    return fail(PMR446_EINVAL, "up-sampler plan not built: arbitrary stage outside (1, 2]");
+  }
+  {  // smallest P <= DSB_T after which the 24-bit phase is back within 1/16 of a bank row: a thread that computes outputs k, k + P,
+     // k + 2P, ... keeps its bank row in registers (x1.92: P = 48, drift -16 / 2^24 per period)
+    const unsigned tol = (1u << (24 - b->up.bits)) / 16;
+    b->arb_period = 32;
+    for (int P = 1; P <= DSB_T; P++) {
+      const unsigned r = (unsigned)(((unsigned long long)P * b->up.step) & 0xffffffu);
+      if (r <= tol || (1u << 24) - r <= tol) { b->arb_period = P; break; }
+    }
+  }
   b->max_res = b->fe.max_out_per_chunk();
   const long long max_z = (long long)design::arb_outputs_after((uint64_t)b->max_res, b->up.step) + 2;
   b->max_out = 2 * max_z;
   b->fm_cap = next_pow2(b->max_res + 64);
-  b->z_cap = next_pow2(max_z + 64);
   std::vector<float> rows((size_t)b->up.npfb * 16, 0.0f);
   for (unsigned i = 0; i < b->up.npfb; i++)
     for (unsigned k = 0; k < 14; k++) rows[(size_t)i * 16 + k] = b->up.pfb[(size_t)i * 14 + k];
-  if ((rc = b->d_fm.alloc_zero((size_t)b->S * b->fm_cap * 4)) || (rc = b->d_z.alloc_zero((size_t)b->S * b->z_cap * 4)) ||
+  if ((rc = b->d_fm.alloc_zero((size_t)b->S * b->fm_cap * 4)) ||
       (rc = b->d_pfb_up.alloc(rows.size() * 4))) {
     dsd446_batch_destroy(b);
     return rc;
@@ -102,7 +115,6 @@ extern "C" int dsd446_batch_reset(dsd446_batch* b) {
   if (int rc = b->fe.reset()) return rc;
   b->n_z = 0;
   CUDA_TRY(cudaMemset(b->d_fm.p, 0, b->d_fm.bytes));
-  CUDA_TRY(cudaMemset(b->d_z.p, 0, b->d_z.bytes));
   CUDA_TRY(cudaDeviceSynchronize());   // see pmr446_batch_reset
   return PMR446_OK;
 }
@@ -135,24 +147,26 @@ extern "C" int dsd446_batch_execute_device(dsd446_batch* b, const void* iq, long
                                                                  (float2*)out->res, out->res_ld);
     if (out->fm) gather_ring_kernel<float><<<g, 256, 0, st>>>((const float*)b->d_fm.p, b->fm_cap, b->fm_cap - 1, r0, ny, out->fm, out->res_ld);
   }
-  if (k1 > k0) {                                              // :170-175
-    dim3 g((unsigned)((k1 - k0 + 255) / 256), S);
-    dim3 ga((unsigned)((k1 - k0 + 256 * DSD_RB - 1) / (256 * DSD_RB)), S);
-    dsd_arb_kernel<<<ga, 256, 0, st>>>((const float*)b->d_fm.p, b->fm_cap, b->fm_cap - 1, (float*)b->d_z.p, b->z_cap, b->z_cap - 1, k0, k1,
-                                      b->up.step, (int)b->up.bits, (const float*)b->d_pfb_up.p);
-    DsdInterpParams ip;
-    ip.z = (const float*)b->d_z.p;
-    ip.z_stride = b->z_cap;
-    ip.z_mask = b->z_cap - 1;
-    ip.k0 = k0;
-    ip.k1 = k1;
-    ip.m = (int)b->up.m[0];
-    memset(ip.hb, 0, sizeof ip.hb);
-    for (size_t j = 0; j < b->up.hb[0].size(); j++) ip.hb[j] = b->up.hb[0][j];
-    ip.audio = out->audio;
-    ip.pcm = out->pcm;
-    ip.out_ld = out->out_ld;
-    if (out->audio || out->pcm) dsd_interp_kernel<<<g, 256, 0, st>>>(ip);
+  if (k1 > k0 && (out->audio || out->pcm)) {                  // :170-175
+    DsdBackendParams bp;
+    memset(&bp, 0, sizeof bp);
+    bp.fm = (const float*)b->d_fm.p;
+    bp.fm_stride = b->fm_cap;
+    bp.fm_mask = b->fm_cap - 1;
+    bp.k0 = k0;
+    bp.k1 = k1;
+    bp.step = b->up.step;
+    bp.bits = (int)b->up.bits;
+    bp.period = b->arb_period;
+    bp.groups = DSB_T / b->arb_period;
+    bp.pfb = (const float*)b->d_pfb_up.p;
+    bp.m = (int)b->up.m[0];
+    for (size_t j = 0; j < b->up.hb[0].size() && j < 20; j++) bp.hb[j] = b->up.hb[0][j];
+    bp.audio = out->audio;
+    bp.pcm = out->pcm;
+    bp.out_ld = out->out_ld;
+    dim3 g((unsigned)((k1 - k0 + DSB_KB - 1) / DSB_KB), S);
+    dsd_backend_kernel<<<g, DSB_T, 0, st>>>(bp);
   }
   b->n_z = k1;
   CUDA_TRY(cudaGetLastError());
