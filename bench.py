@@ -54,7 +54,7 @@ KERNELS_FUSED = {
                  "flop": (19.2 + 31.2 + 25.2 + 24.6 + 11.2) / 2.4, "bytes": 2.0 + 0.2e6 * 8 / 2.4e6},
     "channelize": {"what": "channelize16_kernel: DC zero-input correction, NCO mix, 16 x 26-tap polyphase bank, 16-point DFT, FM discriminator",
                    "flop": (1.2 + 20.8 + 4.0 + 3.8) / 2.4, "bytes": 0.2e6 * 8 / 2.4e6 + 0.2e6 * 4 / 2.4e6},
-    "audio": {"what": "audio_fft_kernel: 377-tap CTCSS high-pass FIR + gain + de-emphasis + s16 by 4096-point overlap-save "
+    "audio": {"what": "audio_fft4_kernel: 377-tap CTCSS high-pass FIR + gain + de-emphasis + s16 by 4096-point overlap-save, four channel rows per block "
                       "(credit = direct-form count of SURVEY 8d; see executed_*)",
               "flop": (150.8 + 1.0) / 2.4, "bytes": 0.2e6 * 4 / 2.4e6 + 0.2e6 * 2 / 2.4e6},
 }
@@ -483,8 +483,8 @@ def run_ours(args, rank, world, local_rank):
 OTHER = {
     "cfg1": {"workload": "configs[0] scaled out: 1024 x 1.024 Msps cu8 PMR446 captures x 16 channels, 1 000 000 samples per stream per step "
                          "(the reference's own rate)", "streams": 1024, "fs": 1024000, "n": 1000000, "flop": 237.8, "bytes": 2.39, "kind": "pmr", "fmt": 1},
-    "cfg2": {"workload": "configs[1] scaled out: 1024 x 2.4 Msps cu8 captures through the dsd_in chain -> 48 kHz s16, 1 200 000 samples per stream per step",
-             "streams": 1024, "fs": 2400000, "n": 1200000, "flop": 35.6, "bytes": 2.094, "kind": "dsd", "fmt": 1},
+    "cfg2": {"workload": "configs[1] scaled out: 1024 x 2.4 Msps cu8 captures through the dsd_in chain -> 48 kHz s16, 1 s of signal (2 400 000 samples) per stream per step",
+             "streams": 1024, "fs": 2400000, "n": 2400000, "flop": 35.6, "bytes": 2.094, "kind": "dsd", "fmt": 1},
     "cfg4": {"workload": "configs[3]: 4 x 20 Msps cf32 captures, 1600-channel 12.5 kHz PFB + per-channel NBFM demod + W=1600 waterfall, 0.1 s per step",
              "streams": 4, "fs": 20000000, "n": 2000000, "flop": 1539.0, "bytes": 10.0, "kind": "wide", "fmt": 0},
     "receiver": {"workload": "reference receiver mode: 1024 x 2.4 Msps cu8, RSSI + squelch/selector + selected-channel audio + CTCSS detector per stream",

@@ -152,6 +152,7 @@ struct DsdBackendParams {
   short* pcm;                // optional [n_streams][out_ld]
   long long out_ld;
 };
+template <int M>   // half-band semi-length known at compile time (unrolled taps from the constant bank), 0 = use p.m
 static __global__ void __launch_bounds__(DSB_T) dsd_backend_kernel(DsdBackendParams p) {
   __shared__ float xs[DSB_XS];
   __shared__ float zs[DSB_KB + DSB_HIST];
@@ -159,7 +160,8 @@ static __global__ void __launch_bounds__(DSB_T) dsd_backend_kernel(DsdBackendPar
   const long long kb = p.k0 + (long long)blockIdx.x * DSB_KB;
   if (kb >= p.k1) return;
   const long long kend = kb + DSB_KB < p.k1 ? kb + DSB_KB : p.k1;
-  const int hist = 2 * p.m - 1;
+  const int m = M ? M : p.m;
+  const int hist = 2 * m - 1;
   const long long ks = kb - hist;                       // first z this block needs (z[k < 0] = 0)
   const long long kf = ks > 0 ? ks : 0;
   const float* f = p.fm + (long long)s * p.fm_stride;
@@ -201,9 +203,14 @@ static __global__ void __launch_bounds__(DSB_T) dsd_backend_kernel(DsdBackendPar
   // ---- phase 2 ----
   for (long long k = kb + threadIdx.x; k < kend; k += DSB_T) {
     const float* q = zs + (int)(k - ks);   // q[-j] = z[k - j]
-    const float y0 = q[-p.m];
+    const float y0 = q[-m];
     float y1 = 0.0f;
-    for (int j = 0; j < 2 * p.m; j++) y1 = fmaf(p.hb[j], q[-j], y1);
+    if (M) {
+#pragma unroll
+      for (int j = 0; j < 2 * M; j++) y1 = fmaf(p.hb[j], q[-j], y1);
+    } else {
+      for (int j = 0; j < 2 * m; j++) y1 = fmaf(p.hb[j], q[-j], y1);
+    }
     const long long o = (long long)s * p.out_ld + 2 * (k - p.k0);
     if (p.audio) {
       p.audio[o] = y0;

@@ -166,7 +166,8 @@ extern "C" int dsd446_batch_execute_device(dsd446_batch* b, const void* iq, long
     bp.pcm = out->pcm;
     bp.out_ld = out->out_ld;
     dim3 g((unsigned)((k1 - k0 + DSB_KB - 1) / DSB_KB), S);
-    dsd_backend_kernel<<<g, DSB_T, 0, st>>>(bp);
+    if (bp.m == 10) dsd_backend_kernel<10><<<g, DSB_T, 0, st>>>(bp);   // the reference's 60 dB plan
+    else dsd_backend_kernel<0><<<g, DSB_T, 0, st>>>(bp);
   }
   b->n_z = k1;
   CUDA_TRY(cudaGetLastError());

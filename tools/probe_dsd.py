@@ -8,7 +8,7 @@ import torch
 
 from sdr_pmr446_b200 import chain, synth
 
-S, fs, n = int(os.environ.get("DSD_STREAMS", "1024")), 2400000, 2400000
+S, fs, n = int(os.environ.get("DSD_STREAMS", "1024")), 2400000, int(os.environ.get("DSD_CHUNK", "2400000"))
 base = torch.from_numpy(synth.cfg2_capture(n=n)).cuda()
 iq = base.unsqueeze(0).repeat(S, 1).contiguous()
 d = chain.DsdBatch(n_streams=S, fs_in=fs, in_fmt=1, max_chunk=n)
