@@ -127,7 +127,21 @@ __device__ __forceinline__ void ldg256_nc(const void* p, unsigned* w) {
 // stages that run once per iteration (m = 10 half-band, resampler) live in shared memory (42 slots x 128 threads x 8 B =
 // 43 KB, thread-private columns: a warp's access to one slot is 256 contiguous bytes), 167 registers, 3 blocks per SM --
 // measured 2.75 ms against 2.68 ms (1024 streams), so occupancy is not what limits this kernel.
-template <int DC, int NB = 2, bool SMH = false, bool LUT = false>
+// CPA = true: the raw bytes travel global -> shared memory with cp.async, FF_CPD sub-blocks ahead (thread-private 32-byte
+// slots, no registers in flight), instead of register loads two sub-blocks ahead behind an L1 prefetch: ptxas sinks those
+// loads to within ~300 instructions of their use and the profile shows them arriving late (5 % of the kernel's stall samples on
+// the first PRMT of a sub-block; l1tex hit rate 10 %: the L1 prefetch does not hold).
+constexpr int FF_CPD = 6;
+// src_bytes = 0 reads nothing and zero-fills: the guard costs no branch, the iteration stays ONE basic block
+__device__ __forceinline__ void cp_async16(unsigned smem, const void* gmem, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ uint4 lds128_v(unsigned smem) {   // volatile: stays behind the wait_group in front of it
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem));
+  return v;
+}
+template <int DC, int NB = 2, bool SMH = false, bool LUT = false, bool CPA = false>
 __global__ void __launch_bounds__(FF_THREADS, NB) fused_frontend_kernel(FusedParams fp) {
   extern __shared__ __align__(16) char ff_lut[];   // LUT only: FF_LUT_BYTES of dynamic shared memory
   const unsigned lane4 = (threadIdx.x & 31u) * 4u;
@@ -200,10 +214,31 @@ __global__ void __launch_bounds__(FF_THREADS, NB) fused_frontend_kernel(FusedPar
   auto prefetch = [&](int sbi) {
     if (sbi >= ld.fast_lo && sbi < ld.fast_hi) asm volatile("prefetch.global.L1 [%0];" ::"l"(ld.fp + (size_t)sbi * (2 * FF_SUB)));
   };
+  // CPA: slot k of the thread = two 16-byte pieces at stage[(2 k + h) * blockDim.x + threadIdx.x]; sub-block sbi uses slot
+  // sbi mod FF_CPD = 3 (it & 1) + sub.  One commit group per sub-block step (empty when the sub-block is not a whole aligned
+  // group of the chunk), so "all but the newest FF_CPD - 1 groups" is always the group of the sub-block about to be read.
+  const unsigned stage = (unsigned)__cvta_generic_to_shared(ff_lut) + 16u * threadIdx.x, spitch = 16u * blockDim.x;
+  auto cp_issue = [&](int sbi, int slot) {
+    const bool ok = sbi >= ld.fast_lo && sbi < ld.fast_hi;
+    const uint8_t* g = ok ? ld.fp + (size_t)sbi * (2 * FF_SUB) : ld.cur;
+    cp_async16(stage + (unsigned)(2 * slot) * spitch, g, ok ? 16 : 0);
+    cp_async16(stage + (unsigned)(2 * slot + 1) * spitch, g + 16, ok ? 16 : 0);
+    asm volatile("cp.async.commit_group;");
+  };
+  auto cp_take = [&](int sbi, int slot, Raw<SRC_CU8, FF_SUB>& r) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(FF_CPD - 1));
+    const uint4 a = lds128_v(stage + (unsigned)(2 * slot) * spitch), b = lds128_v(stage + (unsigned)(2 * slot + 1) * spitch);
+    r.w[0] = a.x; r.w[1] = a.y; r.w[2] = a.z; r.w[3] = a.w; r.w[4] = b.x; r.w[5] = b.y; r.w[6] = b.z; r.w[7] = b.w;
+  };
+  if (CPA) {
 #pragma unroll
-  for (int i = 2; i < FF_PF; i++) prefetch(i);
-  fetch(0, raw[0]);
-  if (n_sub > 1) fetch(1, raw[1]);
+    for (int i = 0; i < FF_CPD; i++) cp_issue(i, i);
+  } else {
+#pragma unroll
+    for (int i = 2; i < FF_PF; i++) prefetch(i);
+    fetch(0, raw[0]);
+    if (n_sub > 1) fetch(1, raw[1]);
+  }
   const float2 cpole = make_float2(1.0f - p.alpha, 1.0f - p.alpha);   // exact: alpha is 1 - fl(1 - alpha_nominal)
 
   // One iteration = 48 input samples.  FAST: all three sub-blocks are whole aligned 32-byte groups of the current chunk --
@@ -215,8 +250,13 @@ __global__ void __launch_bounds__(FF_THREADS, NB) fused_frontend_kernel(FusedPar
 #pragma unroll
     for (int sub = 0; sub < 3; sub++) {
       const int sbi = 3 * it + sub;
-      if (sbi + FF_PF < n_sub) prefetch(sbi + FF_PF);
-      if (sbi + 2 < n_sub) fetch(sbi + 2, raw[(sub + 2) % 3]);   // two sub-blocks ahead
+      const int slot = 3 * (it & 1) + sub;
+      if (CPA) {
+        cp_take(sbi, slot, raw[sub]);
+      } else {
+        if (sbi + FF_PF < n_sub) prefetch(sbi + FF_PF);
+        if (sbi + 2 < n_sub) fetch(sbi + 2, raw[(sub + 2) % 3]);   // two sub-blocks ahead
+      }
       float2 x[FF_SUB];
       if (FAST) {
 #pragma unroll
@@ -231,6 +271,7 @@ __global__ void __launch_bounds__(FF_THREADS, NB) fused_frontend_kernel(FusedPar
         for (int i = 0; i < FF_SUB; i++)   // X = (x - c0') * 128, exact (a sample) or CU8_XBIAS (a zero: before the stream start)
           x[i] = XU ? make_float2(fmaf(xr[i], 128.0f, CU8_XBIAS), fmaf(xi[i], 128.0f, CU8_XBIAS)) : make_float2(xr[i], xi[i]);
       }
+      if (CPA) cp_issue(sbi + FF_CPD, slot);   // refill the slot just emptied (its words are in x by now)
       if (DC != DC_NONE) {
         // A.1 dc blocker, zero-state part: y = x - alpha v[n-1], v[n] = (1 - alpha) v[n-1] + x.  Only the one-FFMA2
         // recurrence of v is serial; the outputs hang off it.

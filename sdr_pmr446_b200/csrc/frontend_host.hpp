@@ -562,6 +562,8 @@ struct Frontend {
             if (on) cudaFuncSetAttribute(fused_frontend_kernel<DC_ZSR, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_LUT_BYTES);
             return on;
           }();
+          // raw bytes staged global -> shared memory by cp.async six sub-blocks ahead (2.456 vs 2.486 ms); PMR446_FF_CPA=0: register loads behind an L1 prefetch
+          static const bool cpa = !(getenv("PMR446_FF_CPA") && atoi(getenv("PMR446_FF_CPA")) == 0);
           static const int thr_env = getenv("PMR446_FF_THREADS") ? atoi(getenv("PMR446_FF_THREADS")) : 0;   // tuning probe: 32 / 64
           // 32-thread blocks: the same 8 warps per SM, but the 10.6 "waves" of 128-thread blocks end in a shorter tail (2.62 vs 2.68 ms)
           const int thr = smem3 ? FF_THREADS : ((thr_env == 64 || thr_env == 128) ? thr_env : 32);
@@ -569,6 +571,7 @@ struct Frontend {
           if (L.dc != DC_ZSR) fused_frontend_kernel<DC_NONE><<<fblocks, thr, 0, st>>>(fp);
           else if (smem3) fused_frontend_kernel<DC_ZSR, 3, true><<<blocks, FF_THREADS, 0, st>>>(fp);
           else if (lut_cvt) fused_frontend_kernel<DC_ZSR, 2, false, true><<<fblocks, thr, FF_LUT_BYTES, st>>>(fp);
+          else if (cpa) fused_frontend_kernel<DC_ZSR, 2, false, false, true><<<fblocks, thr, (size_t)FF_CPD * 32 * thr, st>>>(fp);
           else fused_frontend_kernel<DC_ZSR><<<fblocks, thr, 0, st>>>(fp);
           *launches += 1;
           tm->mark(st, TM_CASCADE0);
