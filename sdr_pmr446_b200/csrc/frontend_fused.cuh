@@ -348,8 +348,10 @@ struct Front6Params {
 };
 constexpr int F6_G = 64, F6_D = 64;
 
-template <int DC, int ME, int MF>
+constexpr int F6_CPD = 8;   // cp.async depth in sub-blocks (two iterations), see fused_frontend_kernel<..., CPA>
+template <int DC, int ME, int MF, bool CPA = false>
 __global__ void __launch_bounds__(FF_THREADS, 2) front6_kernel(Front6Params fp) {
+  extern __shared__ __align__(16) char f6_stage[];   // CPA: F6_CPD x 32 bytes per thread
   const CascadeParams& p = fp.c;
   long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= (long long)p.n_streams * p.nseg) return;
@@ -397,10 +399,28 @@ __global__ void __launch_bounds__(FF_THREADS, 2) front6_kernel(Front6Params fp) 
   auto prefetch = [&](int sbi) {
     if (sbi >= ld.fast_lo && sbi < ld.fast_hi) asm volatile("prefetch.global.L1 [%0];" ::"l"(ld.fp + (size_t)sbi * (2 * FF_SUB)));
   };
+  const unsigned stage = (unsigned)__cvta_generic_to_shared(f6_stage) + 16u * threadIdx.x, spitch = 16u * blockDim.x;
+  auto cp_issue = [&](int sbi, int slot) {
+    const bool ok = sbi >= ld.fast_lo && sbi < ld.fast_hi;
+    const uint8_t* g = ok ? ld.fp + (size_t)sbi * (2 * FF_SUB) : ld.cur;
+    cp_async16(stage + (unsigned)(2 * slot) * spitch, g, ok ? 16 : 0);
+    cp_async16(stage + (unsigned)(2 * slot + 1) * spitch, g + 16, ok ? 16 : 0);
+    asm volatile("cp.async.commit_group;");
+  };
+  auto cp_take = [&](int slot, Raw<SRC_CU8, FF_SUB>& r) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(F6_CPD - 1));
+    const uint4 a = lds128_v(stage + (unsigned)(2 * slot) * spitch), b = lds128_v(stage + (unsigned)(2 * slot + 1) * spitch);
+    r.w[0] = a.x; r.w[1] = a.y; r.w[2] = a.z; r.w[3] = a.w; r.w[4] = b.x; r.w[5] = b.y; r.w[6] = b.z; r.w[7] = b.w;
+  };
+  if (CPA) {
 #pragma unroll
-  for (int i = 2; i < FF_PF; i++) prefetch(i);
-  fetch(0, raw[0]);
-  if (n_sub > 1) fetch(1, raw[1]);
+    for (int i = 0; i < F6_CPD; i++) cp_issue(i, i);
+  } else {
+#pragma unroll
+    for (int i = 2; i < FF_PF; i++) prefetch(i);
+    fetch(0, raw[0]);
+    if (n_sub > 1) fetch(1, raw[1]);
+  }
 
   HbPair<3, 4> sc4;   // stages 3 and 4 run per HALF iteration (32 inputs): shorter live ranges than 16-sample staging arrays
   HbPair<3, 2> sd2;
@@ -415,8 +435,13 @@ __global__ void __launch_bounds__(FF_THREADS, 2) front6_kernel(Front6Params fp) 
       for (int s2 = 0; s2 < 2; s2++) {
         const int sub = 2 * half + s2;
         const int sbi = 4 * it + sub;
-        if (sbi + FF_PF < n_sub) prefetch(sbi + FF_PF);
-        if (sbi + 2 < n_sub) fetch(sbi + 2, raw[(sub + 2) % 4]);
+        const int slot = 4 * (it & 1) + sub;
+        if (CPA) {
+          cp_take(slot, raw[sub]);
+        } else {
+          if (sbi + FF_PF < n_sub) prefetch(sbi + FF_PF);
+          if (sbi + 2 < n_sub) fetch(sbi + 2, raw[(sub + 2) % 4]);
+        }
         float2 x[FF_SUB];
         if (FAST) {
 #pragma unroll
@@ -431,6 +456,7 @@ __global__ void __launch_bounds__(FF_THREADS, 2) front6_kernel(Front6Params fp) 
           for (int i = 0; i < FF_SUB; i++)
             x[i] = XU ? make_float2(fmaf(xr[i], 128.0f, CU8_XBIAS), fmaf(xi[i], 128.0f, CU8_XBIAS)) : make_float2(xr[i], xi[i]);
         }
+        if (CPA) cp_issue(sbi + F6_CPD, slot);
         if (DC != DC_NONE) {
 #pragma unroll
           for (int i = 0; i < FF_SUB; i++) {

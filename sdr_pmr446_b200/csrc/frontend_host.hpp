@@ -525,7 +525,11 @@ struct Frontend {
           memcpy(fp.hb5, L.hb[4], sizeof fp.hb5);
           memcpy(fp.hb6, L.hb[5], sizeof fp.hb6);
           const bool e3 = L.ms[4] == 3;
-          if (L.dc == DC_ZSR && e3) front6_kernel<DC_ZSR, 3, 5><<<blocks, FF_THREADS, 0, st>>>(fp);
+          static const bool f6_cpa = !(getenv("PMR446_F6_CPA") && atoi(getenv("PMR446_F6_CPA")) == 0);   // cp.async staging as in the fused kernel (2.90 -> 2.87 ms per dsd_in step); 0: register loads
+          const size_t f6_smem = (size_t)F6_CPD * 32 * FF_THREADS;
+          if (L.dc == DC_ZSR && e3 && f6_cpa) front6_kernel<DC_ZSR, 3, 5, true><<<blocks, FF_THREADS, f6_smem, st>>>(fp);
+          else if (L.dc == DC_ZSR && f6_cpa) front6_kernel<DC_ZSR, 5, 10, true><<<blocks, FF_THREADS, f6_smem, st>>>(fp);
+          else if (L.dc == DC_ZSR && e3) front6_kernel<DC_ZSR, 3, 5><<<blocks, FF_THREADS, 0, st>>>(fp);
           else if (L.dc == DC_ZSR) front6_kernel<DC_ZSR, 5, 10><<<blocks, FF_THREADS, 0, st>>>(fp);
           else if (e3) front6_kernel<DC_NONE, 3, 5><<<blocks, FF_THREADS, 0, st>>>(fp);
           else front6_kernel<DC_NONE, 5, 10><<<blocks, FF_THREADS, 0, st>>>(fp);
