@@ -128,6 +128,12 @@ __device__ __forceinline__ void dft16p(float2* v) {
   for (int q1 = 0; q1 < 4; q1++) dft4p(v[4 * q1], v[4 * q1 + 1], v[4 * q1 + 2], v[4 * q1 + 3]);
 }
 
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 template <bool TAPS> struct TapState { float macc[16]; };
 template <> struct TapState<false> {};
 
@@ -420,7 +426,7 @@ __global__ void __launch_bounds__(128, (PIPE || TAPS) ? 3 : 4) channelize16_kern
 #pragma unroll
           for (int c = 0; c < 16; c++) {
             const float2 y = v[af_dig(c)];
-            ta.macc[c] += sqrtf(fmaf(y.x, y.x, y.y * y.y));
+            ta.macc[c] += sqrt_approx(fmaf(y.x, y.x, y.y * y.y));   // MUFU.SQRT, 1 ulp: the RSSI is a mean of 12 500 of these, compared to 1e-3 dB
           }
           if ((kk == k_first || kk == k_last) && tp.edge) {   // one lane of one batch per call
             float2* e = tp.edge + (long long)s * 32;

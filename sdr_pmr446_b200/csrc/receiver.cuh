@@ -188,7 +188,20 @@ static __global__ void __launch_bounds__(64) ctcss_kernel(CtcssParams p) {
     for (int i = j; i < len; i += 64) xs[i] = x[base + i];
     __syncthreads();
     if (j == 0) {   // iirfilt_rrrf DC blocker (Direct Form II): v0 = x - a1 v1 ; y = v0 - v1
-      for (int i = 0; i < len; i++) {
+      // eight samples per trip, loaded before the chain starts: the shared-memory latency stays off the serial mul -> sub path
+      int i = 0;
+      for (; i + 8 <= len; i += 8) {
+        float xv[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) xv[q] = xs[i + q];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const float v0 = __fsub_rn(xv[q], __fmul_rn(p.dc_a1, v1));
+          xs[i + q] = __fsub_rn(v0, v1);
+          v1 = v0;
+        }
+      }
+      for (; i < len; i++) {
         const float v0 = __fsub_rn(xs[i], __fmul_rn(p.dc_a1, v1));
         xs[i] = __fsub_rn(v0, v1);
         v1 = v0;
@@ -201,7 +214,19 @@ static __global__ void __launch_bounds__(64) ctcss_kernel(CtcssParams p) {
     while (i < len) {
       // run to the end of the tile or of the detector block, whichever comes first (uniform over the block)
       const int run = (int)min((unsigned)(len - i), p.block - samp);
-      for (int e = i + run; i < e; i++) {
+      const int e = i + run;
+      for (; i + 8 <= e; i += 8) {   // same recurrence, same order; the eight broadcast loads run ahead of the serial chain
+        float xv[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) xv[q] = xs[i + q];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const float t = u0;
+          u0 = __fsub_rn(__fadd_rn(xv[q], __fmul_rn(coef, u0)), u1);
+          u1 = t;
+        }
+      }
+      for (; i < e; i++) {
         const float t = u0;
         u0 = __fsub_rn(__fadd_rn(xs[i], __fmul_rn(coef, u0)), u1);
         u1 = t;
