@@ -205,6 +205,33 @@ def test_2400k_awkward_chunks_exercise_tile_edges():
     _check(g, [r], [car])
 
 
+def test_2400k_audio_tile_boundaries():
+    """Chunks whose audio length sits exactly on / one past / one short of the fast-convolution tile (3584 samples = 688 128 inputs):
+    the FFT audio kernel counts its tiles from the call's first sample, so these are its full-tile, one-sample-tile and
+    almost-full-tile cases, each starting at a different offset of the discriminator ring."""
+    from oracle import oracle as orc
+    from sdr_pmr446_b200 import chain, synth
+    fs = 2400000
+    sizes = [688128, 688128 + 192, 688128 - 192, 2 * 688128, 192]
+    n = sum(sizes)
+    car = synth.rotated_carriers(3)
+    iq = synth.make_cu8(synth.CaptureSpec(fs=float(fs), carriers=car), n, 449)
+    gpu = chain.PmrBatch(n_streams=1, fs_in=fs, in_fmt=1, audio_gain=1.0, max_chunk=max(sizes))
+    parts, o = [], 0
+    for k in sizes:
+        parts.append(gpu.execute(iq[None, 2 * o:2 * (o + k)]))
+        o += k
+    gpu.close()
+    assert [p["ns"] for p in parts] == [3584, 3585, 3583, 7168, 1]
+    g = {"ny": sum(p["ny"] for p in parts), "ns": sum(p["ns"] for p in parts)}
+    for k in ("res", "chan", "demod", "lpcomp", "audio", "pcm"):
+        g[k] = np.concatenate([p[k] for p in parts], axis=-1)
+    ref = orc.PmrOracle(fs_in=fs, in_fmt=1, audio_gain=1.0, chunk=240000)
+    r = ref.run(iq, 240000)
+    ref.close()
+    _check(g, [r], [car])
+
+
 def test_2400k_cf32_lowpass_pcm_only():
     """cf32 input at 2.4 Msps, audio low-pass on, only s16 requested (the benchmark's output set: FFT audio kernel alone)."""
     from oracle import oracle as orc
