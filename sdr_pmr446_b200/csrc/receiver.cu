@@ -233,7 +233,7 @@ extern "C" int pmr446_receiver_execute_device(pmr446_receiver* r, const void* iq
   cp.power_out = out->ctcss_power;
   cp.status = out->status;
   cp.out_ld = out->ld;
-  ctcss_kernel<<<S, 64, 0, st>>>(cp);
+  ctcss_kernel<<<S, CT_THREADS, 0, st>>>(cp);
   r->launches++;
   CUDA_TRY(cudaGetLastError());
   if (ns_out) *ns_out = ns;

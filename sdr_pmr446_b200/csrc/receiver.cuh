@@ -167,11 +167,40 @@ struct CtcssParams {
 
 constexpr int CT_TILE = 1024;
 
-// one block per stream; thread j < 38 runs tone j over the samples in order, thread 0 also owns the DC blocker output
-static __global__ void __launch_bounds__(64) ctcss_kernel(CtcssParams p) {
-  __shared__ float xs[CT_TILE];
+// One block per stream, three warps: threads j < 38 (warps 0 and 1) run tone j over the samples in order; warp 2 runs the DC
+// blocker -- a serial chain of its own -- one tile AHEAD of them, in the other half of a double buffer, so a tile costs
+// max(DC chain, Goertzel chains) instead of their sum (the two-warp kernel spent 43 % of its time with every tone thread
+// waiting at the barrier behind the DC thread).  Same operations in the same order as before (bit-exact detector).
+constexpr int CT_THREADS = 96;
+__device__ __forceinline__ void ct_dc_tile(float* xs, int len, float a1, float& v1) {
+  // iirfilt_rrrf DC blocker (Direct Form II): v0 = x - a1 v1 ; y = v0 - v1.  Eight samples per trip, loaded before the chain
+  // starts: the shared-memory latency stays off the serial mul -> sub path
+  int i = 0;
+  for (; i + 8 <= len; i += 8) {
+    float xv[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) xv[q] = xs[i + q];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const float v0 = __fsub_rn(xv[q], __fmul_rn(a1, v1));
+      xs[i + q] = __fsub_rn(v0, v1);
+      v1 = v0;
+    }
+  }
+  for (; i < len; i++) {
+    const float v0 = __fsub_rn(xs[i], __fmul_rn(a1, v1));
+    xs[i] = __fsub_rn(v0, v1);
+    v1 = v0;
+  }
+}
+__device__ __forceinline__ void ct_tone_barrier() { asm volatile("bar.sync 1, 64;" ::: "memory"); }   // warps 0 and 1 only
+
+static __global__ void __launch_bounds__(CT_THREADS) ctcss_kernel(CtcssParams p) {
+  __shared__ float xbuf[2][CT_TILE];
   __shared__ float pw[RX_TONES];
+  __shared__ float sh_v1;
   const int s = blockIdx.x, j = threadIdx.x;
+  const bool dc_warp = j >= 64;
   RxState st = p.st[s];
   const int n = (int)(st.sel_f1 - st.sel_f0);
   float* ub = p.u + (long long)s * 3 * RX_TONES;
@@ -182,32 +211,24 @@ static __global__ void __launch_bounds__(64) ctcss_kernel(CtcssParams p) {
   float v1 = st.dc_v1;
   unsigned samp = st.samp;
   const float* x = p.lpcomp + (long long)s * p.ld;
-  for (int base = 0; base < n; base += CT_TILE) {
+  // prologue: tile 0 raw -> xbuf[0], DC on it
+  {
+    const int len0 = min(CT_TILE, n);
+    for (int i = j; i < len0; i += CT_THREADS) xbuf[0][i] = x[i];
+    __syncthreads();
+    if (j == 64) ct_dc_tile(xbuf[0], len0, p.dc_a1, v1);
+    __syncthreads();
+  }
+  for (int base = 0, k = 0; base < n; base += CT_TILE, k++) {
+    float* const xs = xbuf[k & 1];
+    float* const xn = xbuf[(k & 1) ^ 1];
     const int len = min(CT_TILE, n - base);
+    const int len_n = min(CT_TILE, n - base - CT_TILE);           // <= 0: no next tile
+    for (int i = j; i < len_n; i += CT_THREADS) xn[i] = x[base + CT_TILE + i];
     __syncthreads();
-    for (int i = j; i < len; i += 64) xs[i] = x[base + i];
-    __syncthreads();
-    if (j == 0) {   // iirfilt_rrrf DC blocker (Direct Form II): v0 = x - a1 v1 ; y = v0 - v1
-      // eight samples per trip, loaded before the chain starts: the shared-memory latency stays off the serial mul -> sub path
-      int i = 0;
-      for (; i + 8 <= len; i += 8) {
-        float xv[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++) xv[q] = xs[i + q];
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-          const float v0 = __fsub_rn(xv[q], __fmul_rn(p.dc_a1, v1));
-          xs[i + q] = __fsub_rn(v0, v1);
-          v1 = v0;
-        }
-      }
-      for (; i < len; i++) {
-        const float v0 = __fsub_rn(xs[i], __fmul_rn(p.dc_a1, v1));
-        xs[i] = __fsub_rn(v0, v1);
-        v1 = v0;
-      }
-    }
-    __syncthreads();
+    if (dc_warp) {
+      if (j == 64 && len_n > 0) ct_dc_tile(xn, len_n, p.dc_a1, v1);
+    } else {
     if (p.ctcss_in)
       for (int i = j; i < len; i += 64) p.ctcss_in[(long long)s * p.out_ld + base + i] = xs[i];
     int i = 0;
@@ -238,7 +259,7 @@ static __global__ void __launch_bounds__(64) ctcss_kernel(CtcssParams p) {
           ub[2 * RX_TONES + j] = pw[j];
         }
         u0 = u1 = 0.0f;
-        __syncthreads();
+        ct_tone_barrier();
         if (j == 0) {
           float avg = 0.0f, mx = 0.0f;
           int mi = st.max_index;
@@ -251,11 +272,16 @@ static __global__ void __launch_bounds__(64) ctcss_kernel(CtcssParams p) {
           st.max_index = mi;
           st.tone = (avg > 120.0f) && (__fdiv_rn(mx, avg) > 10.0f);
         }
-        __syncthreads();
+        ct_tone_barrier();
         samp = 0;
       }
     }
+    }
+    __syncthreads();   // tile k consumed, tile k + 1 filtered
   }
+  if (j == 64) sh_v1 = v1;
+  __syncthreads();
+  v1 = sh_v1;
   if (tone) { ub[j] = u0; ub[RX_TONES + j] = u1; }
   if (p.power_out && tone) p.power_out[(long long)s * RX_TONES + j] = ub[2 * RX_TONES + j];
   if (j == 0) {
