@@ -218,9 +218,10 @@ __global__ void __launch_bounds__(FF_THREADS, NB) fused_frontend_kernel(FusedPar
   // sbi mod FF_CPD = 3 (it & 1) + sub.  One commit group per sub-block step (empty when the sub-block is not a whole aligned
   // group of the chunk), so "all but the newest FF_CPD - 1 groups" is always the group of the sub-block about to be read.
   const unsigned stage = (unsigned)__cvta_generic_to_shared(ff_lut) + 16u * threadIdx.x, spitch = 16u * blockDim.x;
+  const uint8_t* const cp_dummy = (const uint8_t*)((uintptr_t)ld.cur & ~(uintptr_t)31);
   auto cp_issue = [&](int sbi, int slot) {
     const bool ok = sbi >= ld.fast_lo && sbi < ld.fast_hi;
-    const uint8_t* g = ok ? ld.fp + (size_t)sbi * (2 * FF_SUB) : ld.cur;
+    const uint8_t* g = ok ? ld.fp + (size_t)sbi * (2 * FF_SUB) : cp_dummy;   // zero-size copy: never read, but the address stays 16-byte aligned
     cp_async16(stage + (unsigned)(2 * slot) * spitch, g, ok ? 16 : 0);
     cp_async16(stage + (unsigned)(2 * slot + 1) * spitch, g + 16, ok ? 16 : 0);
     asm volatile("cp.async.commit_group;");
@@ -400,9 +401,10 @@ __global__ void __launch_bounds__(FF_THREADS, 2) front6_kernel(Front6Params fp) 
     if (sbi >= ld.fast_lo && sbi < ld.fast_hi) asm volatile("prefetch.global.L1 [%0];" ::"l"(ld.fp + (size_t)sbi * (2 * FF_SUB)));
   };
   const unsigned stage = (unsigned)__cvta_generic_to_shared(f6_stage) + 16u * threadIdx.x, spitch = 16u * blockDim.x;
+  const uint8_t* const cp_dummy = (const uint8_t*)((uintptr_t)ld.cur & ~(uintptr_t)31);
   auto cp_issue = [&](int sbi, int slot) {
     const bool ok = sbi >= ld.fast_lo && sbi < ld.fast_hi;
-    const uint8_t* g = ok ? ld.fp + (size_t)sbi * (2 * FF_SUB) : ld.cur;
+    const uint8_t* g = ok ? ld.fp + (size_t)sbi * (2 * FF_SUB) : cp_dummy;   // zero-size copy: never read, but the address stays 16-byte aligned
     cp_async16(stage + (unsigned)(2 * slot) * spitch, g, ok ? 16 : 0);
     cp_async16(stage + (unsigned)(2 * slot + 1) * spitch, g + 16, ok ? 16 : 0);
     asm volatile("cp.async.commit_group;");

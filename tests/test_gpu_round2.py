@@ -258,3 +258,38 @@ def test_deferred_dc_correction_path_float_parity():
             assert rel_rms(g["demod"][0, c, sl], r["demod"][c, sl]) < REL_RMS_TOL, ("demod", c)
             dp = np.abs(g["pcm"][0, c, 600:].astype(np.int32) - r["pcm"][c, 600:].astype(np.int32))
             assert dp.max() <= PCM_TOL_LSB, ("pcm", c, int(dp.max()))
+
+
+def test_unaligned_device_buffer_takes_the_guarded_path():
+    """pmr446_batch_execute_device / dsd446_batch_execute_device with a device pointer that is only sample-aligned (2 bytes): no
+    32-byte vector loads, no cp.async of whole sub-blocks -- every sample goes through the guarded loader, and the result must be
+    the aligned run's (same arithmetic, same segment grid: at most the 1 LSB the s16 tolerance allows)."""
+    import torch
+    from sdr_pmr446_b200 import chain, synth
+    fs, n, S = 2400000, 240000, 2
+    caps = [synth.make_cu8(synth.CaptureSpec(fs=float(fs), carriers=synth.rotated_carriers(s)), n, 446 + s) for s in range(S)]
+    iq = torch.from_numpy(np.stack(caps)).cuda()
+    pad = torch.zeros((S, 2 * n + 64), dtype=torch.uint8, device="cuda")
+    shifted = pad[:, 2:2 + 2 * n]
+    shifted.copy_(iq)
+    assert shifted.data_ptr() % 32 == 2
+    res = []
+    for buf in (iq, shifted):
+        b = chain.PmrBatch(n_streams=S, fs_in=fs, in_fmt=1, audio_gain=1.0, max_chunk=n)
+        pcm = torch.zeros((S, 16, b.max_ns), dtype=torch.int16, device="cuda")
+        ny, ns = b.execute_device(buf, n, {"ld": b.max_ns, "pcm": pcm})
+        torch.cuda.synchronize()
+        res.append((ny, ns, pcm[:, :, :ns].cpu().numpy()))
+        b.close()
+    assert res[0][:2] == res[1][:2]
+    assert np.abs(res[0][2].astype(np.int32) - res[1][2].astype(np.int32)).max() <= PCM_TOL_LSB
+    res = []
+    for buf in (iq, shifted):
+        d = chain.DsdBatch(n_streams=S, fs_in=fs, in_fmt=1, max_chunk=n)
+        pcm = torch.zeros((S, d.max_out), dtype=torch.int16, device="cuda")
+        r = d.execute_device(buf, n, pcm=pcm)
+        torch.cuda.synchronize()
+        res.append((r, pcm.cpu().numpy()))
+        d.close()
+    assert res[0][0] == res[1][0]
+    assert np.abs(res[0][1].astype(np.int32) - res[1][1].astype(np.int32)).max() <= PCM_TOL_LSB
