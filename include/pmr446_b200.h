@@ -221,6 +221,7 @@ int dsd446_batch_create(const dsd446_config *cfg, dsd446_batch **out);
 int dsd446_batch_destroy(dsd446_batch *b);
 long long dsd446_batch_max_res(const dsd446_batch *b);   /* res_size, src/dsd_in.c:137 */
 long long dsd446_batch_max_out(const dsd446_batch *b);   /* out_size, :138 */
+int dsd446_batch_last_launches(const dsd446_batch *b);  /* kernels launched by the last execute call (like pmr446_batch_last_launches) */
 int dsd446_batch_execute(dsd446_batch *b, const void *iq, long long iq_stride, unsigned n, const dsd446_outputs *out, unsigned *ny,
                          unsigned *nz);
 int dsd446_batch_execute_device(dsd446_batch *b, const void *iq, long long iq_stride, unsigned n, const dsd446_outputs *out,

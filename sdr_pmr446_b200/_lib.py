@@ -73,7 +73,7 @@ EXPORTS = [
     "pmr446_rx_default_config", "pmr446_receiver_create", "pmr446_receiver_destroy", "pmr446_receiver_max_ns",
     "pmr446_receiver_execute", "pmr446_receiver_execute_device", "pmr446_receiver_last_launches", "pmr446_receiver_reset",
     "dsd446_default_config", "dsd446_batch_create", "dsd446_batch_destroy", "dsd446_batch_max_res",
-    "dsd446_batch_max_out", "dsd446_batch_execute", "dsd446_batch_execute_device", "dsd446_batch_reset",
+    "dsd446_batch_max_out", "dsd446_batch_last_launches", "dsd446_batch_execute", "dsd446_batch_execute_device", "dsd446_batch_reset",
     "pmr446_design_msresamp", "pmr446_design_pfbch", "pmr446_design_asgram_window", "pmr446_design_nco_dtheta",
     "pmr446_count_resampled", "pmr446_describe_frontend",
 ]
@@ -135,6 +135,7 @@ def lib():
         L.dsd446_batch_max_res.restype = C.c_longlong
         L.dsd446_batch_max_out.argtypes = [C.c_void_p]
         L.dsd446_batch_max_out.restype = C.c_longlong
+        L.dsd446_batch_last_launches.argtypes = [C.c_void_p]
         L.dsd446_batch_execute.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_uint, C.POINTER(DsdOutputs),
                                            C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
         L.dsd446_batch_execute_device.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_uint, C.POINTER(DsdOutputs),

@@ -287,6 +287,10 @@ class DsdBatch:
     def reset(self):
         check(lib().dsd446_batch_reset(self.h), "dsd446_batch_reset")
 
+    @property
+    def last_launches(self):
+        return lib().dsd446_batch_last_launches(self.h)
+
     def execute(self, iq):
         iq = np.ascontiguousarray(iq)
         if iq.ndim == 1:

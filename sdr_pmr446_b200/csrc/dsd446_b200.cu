@@ -23,6 +23,7 @@ struct dsd446_batch {
   design::MsresampPlan up;        // interpolating msresamp_rrrf plan
   DevBuf d_fm, d_pfb_up;
   long long fm_cap = 0;
+  int launches = 0;          // kernels launched by the last execute call
   int arb_period = 32;       // (near-)period of the up-sampler's phase sequence in outputs (dsd_backend_kernel)
   long long n_z = 0;              // arbitrary-resampler outputs produced so far
   long long max_res = 0, max_out = 0;
@@ -107,6 +108,7 @@ extern "C" int dsd446_batch_create(const dsd446_config* cfg, dsd446_batch** out)
 
 extern "C" long long dsd446_batch_max_res(const dsd446_batch* b) { return b ? b->max_res : 0; }
 extern "C" long long dsd446_batch_max_out(const dsd446_batch* b) { return b ? b->max_out : 0; }
+extern "C" int dsd446_batch_last_launches(const dsd446_batch* b) { return b ? b->launches : 0; }
 
 extern "C" int dsd446_batch_reset(dsd446_batch* b) {
   if (!b) return fail(PMR446_EINVAL, "null handle");
@@ -143,6 +145,7 @@ extern "C" int dsd446_batch_execute_device(dsd446_batch* b, const void* iq, long
     dim3 g((unsigned)((ny + 255) / 256), S);
     dsd_freqdem_kernel<<<g, 256, 0, st>>>((const float2*)b->fe.out.p, b->fe.out_cap, b->fe.out_cap - 1, (float*)b->d_fm.p, b->fm_cap,
                                           b->fm_cap - 1, r0, r1, (float)(1.0f / (2 * M_PI * b->cfg.kf)));   // :169
+    launches += 1 + (out->res ? 1 : 0) + (out->fm ? 1 : 0);
     if (out->res) gather_ring_kernel<float2><<<g, 256, 0, st>>>((const float2*)b->fe.out.p, b->fe.out_cap, b->fe.out_cap - 1, r0, ny,
                                                                  (float2*)out->res, out->res_ld);
     if (out->fm) gather_ring_kernel<float><<<g, 256, 0, st>>>((const float*)b->d_fm.p, b->fm_cap, b->fm_cap - 1, r0, ny, out->fm, out->res_ld);
@@ -168,7 +171,9 @@ extern "C" int dsd446_batch_execute_device(dsd446_batch* b, const void* iq, long
     dim3 g((unsigned)((k1 - k0 + DSB_KB - 1) / DSB_KB), S);
     if (bp.m == 10) dsd_backend_kernel<10><<<g, DSB_T, 0, st>>>(bp);   // the reference's 60 dB plan
     else dsd_backend_kernel<0><<<g, DSB_T, 0, st>>>(bp);
+    launches++;
   }
+  b->launches = launches;
   b->n_z = k1;
   CUDA_TRY(cudaGetLastError());
   if (ny_out) *ny_out = (unsigned)ny;
