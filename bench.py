@@ -314,6 +314,9 @@ def run_ours(args, rank, world, local_rank):
 
     # ---------------- device-resident arm ("value") ----------------
     launches = 0
+    # ranks finish their set-up (synthetic captures, pinned buffers) seconds apart: meet BEFORE the warm-up, so that no GPU sits idle --
+    # and drops its clocks -- between its warm-up steps and the timed region (seen at 8 GPUs: three ranks at 4.2-4.4 ms, five at 4.10)
+    barrier()
     for _ in range(args.warmup):
         batch.execute_device(iq_dev, n, outs)
     batch.timing(True)
