@@ -175,3 +175,15 @@ def test_every_decimating_rate_has_a_frontend_plan():
             rc = L.pmr446_describe_frontend(np.float32(r), 60.0, fmt, 1, buf, 256)
             assert rc == 0, (r, fmt, L.pmr446_last_error())
     assert L.pmr446_describe_frontend(np.float32(1.5), 60.0, 0, 1, buf, 256) != 0      # interpolation is msresamp_rrrf's job (dsd_in)
+
+
+def test_makefile_lists_every_kernel_header():
+    """A header missing from HDRS means an edit to it does not rebuild the library that travels to the GPU box."""
+    import glob
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "sdr_pmr446_b200", "csrc")
+    mk = open(os.path.join(root, "Makefile")).read().replace("\\\n", " ")
+    hdrs = set(re.search(r"^HDRS\s*=\s*(.*)$", mk, re.M).group(1).split())
+    have = {os.path.basename(p) for p in glob.glob(os.path.join(root, "*.cuh")) + glob.glob(os.path.join(root, "*.hpp"))}
+    assert have <= hdrs, sorted(have - hdrs)
